@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py — D2Q9 fp64 MLUPS of the fused time step on N B200s, with roofline, e2e and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--size S] [--strong] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[4]): fully periodic shear-wave lattice, rho0 = 1,
+u0 = (0.01 sin(2 pi y / ly), 0), omega = 1.0, f0 = f_eq; weak scaling = 16384 x 16384 cells PER GPU (1-D slabs
+along the slow axis, ghost rows stored by the neighbour's kernel over NVLink), strong = 32768 x 32768 total.
+One "step" = one reference time step over the whole lattice. MLUPS = cells * steps / seconds / 1e6, whole job.
+
+Prints ONE JSON line (rank 0). Keys beyond the base contract: "roofline", "cpu_baseline" (see README/DESIGN.md).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_UPDATE = 144.0   # 9 populations x 8 B read + 9 x 8 B written
+EPS, OMEGA = 0.01, 1.0
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as fh:
+            return float(json.load(fh)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs, device copy)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            p = [c.strip() for c in r.split(',')]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), p[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference's numpy algorithm (the reference itself is Python and does not
+# travel to the GPU box; oracle/lbm_numpy.py is pinned to it bit-for-bit by tests/test_oracle_golden.py)
+# ---------------------------------------------------------------------------------------------------------
+def cpu_reference_mlups(n, steps, warmup):
+    from oracle import lbm_numpy as onp
+    rho, u = onp.sinusoidal_velocity_x((n, n), EPS)
+    f = onp.equilibrium(rho, u)
+    for _ in range(warmup):
+        f, rho, u = onp.step(f, rho, u, OMEGA)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        f, rho, u = onp.step(f, rho, u, OMEGA)
+    dt = time.perf_counter() - t0
+    return n * n * steps / dt / 1e6, dt
+
+
+def cpu_model():
+    try:
+        with open('/proc/cpuinfo') as fh:
+            for line in fh:
+                if line.startswith('model name'):
+                    return line.split(':', 1)[1].strip()
+    except Exception:
+        pass
+    return 'unknown'
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU algorithm (oracle port, kind "port") on the host cores; each step a
+    bounded sample of the workload (one time step on an n x n lattice, n = 2048)."""
+    if rank != 0:
+        return
+    n = args.cpu_size
+    mlups, dt = cpu_reference_mlups(n, args.steps, args.warmup)
+    sample = (f'{n}x{n} periodic shear wave (same fields/omega as the GPU arm, which runs {args.size}^2 per GPU; the '
+              f'numpy path needs ~400 B/cell so the full size does not fit/finish), {args.steps} steps, 1 process: numpy '
+              f'ufuncs are single-threaded; host has {os.cpu_count()} logical cores, {cpu_model()}')
+    line = {
+        'impl': 'reference', 'metric': 'D2Q9 fp64 MLUPS', 'value': mlups, 'unit': 'MLUPS', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': workload_config(args, 1),
+        'cpu_baseline': {'value': mlups, 'unit': 'MLUPS', 'cores': 1, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': mlups, 'unit': 'MLUPS', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    if args.strong:
+        wl = f'strong scaling: {args.size}x{args.size} total periodic shear-wave lattice over {world} GPU(s)'
+    else:
+        wl = f'weak scaling: {args.size}x{args.size} periodic shear-wave lattice per GPU ({args.size * world}x{args.size} total)'
+    return {'workload': wl, 'lattice_per_gpu': [args.size // world if args.strong else args.size, args.size],
+            'omega': OMEGA, 'epsilon': EPS, 'decomposition': f'{world}x1 slabs along the slow axis, 1 ghost row each side'
+            if world > 1 else 'single block, periodic wrap in-kernel',
+            'l2': 'populations are 19.3 GB per GPU per buffer >> 126 MB L2; no flush needed'}
+
+
+# ---------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--size', type=int, default=16384, help='lattice edge per GPU (weak) or total (with --strong)')
+    ap.add_argument('--strong', action='store_true')
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--cpu-size', type=int, default=2048)
+    ap.add_argument('--cpu-steps', type=int, default=4)
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--e2e-size', type=int, default=0, help='lattice edge of the e2e job (default: --size)')
+    args = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        return run_reference(args, rank)
+    assert args.warmup >= 3, 'timing hygiene: at least 3 warm-up steps'
+
+    import torch
+    import torch.distributed as dist
+    from lattice_boltzmann_parallel_solver_b200 import _native as N
+    from lattice_boltzmann_parallel_solver_b200 import dist as ldist
+    from lattice_boltzmann_parallel_solver_b200 import parallelization_utils as par
+    from lattice_boltzmann_parallel_solver_b200.engine import Lattice
+
+    torch.cuda.set_device(local)
+    N.set_device(local)
+    if world > 1:
+        ldist.ensure_process_group('nccl')
+    assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}'
+
+    ny = args.size
+    nx_local = args.size // world if args.strong else args.size
+    nx_global = nx_local * world
+    prof = EPS * np.sin(np.divide(2 * np.pi * np.arange(ny), ny))   # initial_values.py:83-88
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    if world == 1:
+        lat = Lattice(nx_local, ny)
+    else:
+        lat = Lattice(nx_local + 2, ny, ghost=(1, 0))
+        cart = ldist.comm_world().Create_cart(dims=[world, 1], periods=[True, True])
+        par.communication(cart).attach(lat)
+    lat.load_equilibrium(OMEGA, ux_y=prof)
+    barrier()
+
+    stream = torch.cuda.ExternalStream(lat.stream)
+    lat.run(args.warmup)
+    lat.sync()
+    barrier()
+    l0 = lat.launches
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    barrier()
+    e0.record(stream)
+    lat.run(args.steps)
+    e1.record(stream)
+    lat.sync()
+    torch.cuda.synchronize()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = lat.launches - l0
+    if world > 1:
+        t = torch.tensor([ms], device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    cells_total = nx_global * ny
+    mlups = cells_total * args.steps / (ms * 1e-3) / 1e6
+
+    # roofline of the dominant kernel (k_step, interior launch): algorithmic bytes per launch / mean launch time
+    peak, peak_src = measured_peak_gbs()
+    per_gpu_cells = nx_local * ny
+    achieved = per_gpu_cells * ALGO_BYTES_PER_UPDATE / (ms * 1e-3 / args.steps) / 1e9
+    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': None, 'peak_source': peak_src,
+                'kernel': 'k_step<MASK=0,HALO=0,FINAL=0,LIST=0>',
+                'algorithmic_bytes_per_launch': per_gpu_cells * ALGO_BYTES_PER_UPDATE,
+                'mlups_at_peak': peak * 1e9 / ALGO_BYTES_PER_UPDATE / 1e6,
+                'frac_of_nominal_8TBps': achieved / 8000.0}
+    prof_path = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(prof_path):
+        try:
+            with open(prof_path) as fh:
+                roofline['traffic'] = json.load(fh).get('dram_bytes_per_launch_16384')
+        except Exception:
+            pass
+
+    # ---- e2e: the whole job through the reference-shaped API with HOST buffers ------------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, lat, world, rank, nx_local, ny, prof, barrier)
+    lat.close()
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        v, dt = cpu_reference_mlups(args.cpu_size, args.cpu_steps, 1)
+        cpu = {'value': v, 'unit': 'MLUPS', 'cores': 1, 'kind': 'port',
+               'sample': f'{args.cpu_size}x{args.cpu_size} periodic shear wave, {args.cpu_steps} steps after 1 warm-up, '
+                         f'oracle/lbm_numpy.py (numpy restatement of the reference, single-threaded ufuncs); host: '
+                         f'{os.cpu_count()} logical cores, {cpu_model()}; {dt:.1f} s'}
+    if rank == 0:
+        line = {
+            'metric': 'D2Q9 fp64 MLUPS', 'value': mlups, 'unit': 'MLUPS', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'scaling': 'strong' if args.strong else 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': workload_config(args, world), 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
+            'roofline': roofline, 'cpu_baseline': cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(args, lat, world, rank, nx_local, ny, prof, barrier):
+    """Whole job through the public API the reference's drivers use, starting and ending in HOST memory: upload of
+    the rank's (f, density, velocity) from pinned host buffers, K calls of lattice_boltzmann_step's engine with a
+    device->host read of the step's observable (probe velocity, experiments.py:703-704) after EVERY step, and the
+    final device->host copy of f, density, velocity. Bytes per step = totals / K."""
+    import torch
+    import torch.distributed as dist
+    from lattice_boltzmann_parallel_solver_b200 import _native as N
+    n = args.e2e_size or args.size
+    if n != args.size or world > 1 and args.strong:
+        return None
+    g = lat.ghost[0]
+    NX = nx_local + 2 * g
+    cells = NX * ny
+    try:
+        hf = torch.empty((NX, ny, 9), dtype=torch.float64, pin_memory=True).numpy()
+        hr = torch.empty((NX, ny), dtype=torch.float64, pin_memory=True).numpy()
+        hu = torch.empty((NX, ny, 2), dtype=torch.float64, pin_memory=True).numpy()
+    except RuntimeError as e:   # not enough pinnable host memory on this box
+        return {'value': None, 'unit': 'MLUPS', 'h2d_bytes_per_step': None, 'd2h_bytes_per_step': None, 'skipped': str(e)[:120]}
+    # host-side initial state = what the reference driver builds (experiments.py:121-122); built through the device
+    # because a 16384^2 numpy equilibrium would take minutes of host time outside the timed region
+    # t=0 arrays on the host: rho = 1, u = profile, f = f_eq (bit-identical to the numpy expression)
+    hr[...] = 1.0
+    hu[..., 0] = prof[None, :]
+    hu[..., 1] = 0.0
+    lib = N.load()
+    row_rho, row_u = np.ones((1, ny)), np.zeros((1, ny, 2))
+    row_u[0, :, 0] = prof
+    row_f = np.empty((1, ny, 9))
+    N.check(lib.lbm_equilibrium(lat.device, ny, N.dptr(row_rho), N.dptr(row_u), N.dptr(row_f)))
+    hf[...] = row_f
+    px, py = NX // 2, ny // 4
+    lat.probe(px, py, capacity=8)
+    K = args.steps
+    sink = np.empty((1, 2))
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    lat.load(hf, hr, hu, OMEGA)                       # H2D: 96 B per cell
+    barrier()
+    for k in range(K):
+        lat.run(1)
+        sink[...] = lat.probe_read(k + 1, 1)          # D2H: 16 B, every step (synchronises)
+    of, orho, ou = hf, hr, hu
+    N.check(lib.lbm_materialize(lat._ctx, N.dptr(of), N.dptr(orho), N.dptr(ou)))   # D2H: 96 B per cell
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    total_cells = nx_local * world * ny
+    return {'value': total_cells * K / dt / 1e6, 'unit': 'MLUPS',
+            'h2d_bytes_per_step': cells * 96.0 / K, 'd2h_bytes_per_step': cells * 96.0 / K + 16.0,
+            'job': f'upload f,rho,u from pinned host memory ({cells * 96 / 1e9:.1f} GB per GPU), {K} steps each followed by '
+                   f'a 16-byte probe read, download f,rho,u; wall clock {dt:.2f} s, max over ranks',
+            'steps': K}
+
+
+if __name__ == '__main__':
+    main()

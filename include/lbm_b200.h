@@ -1,0 +1,178 @@
+/*
+ * lbm_b200.h — C-ABI of the B200-native D2Q9 fp64 lattice Boltzmann time step.
+ *
+ * Drop-in boundary for ONE hot path of SimonSchrodi/lattice_boltzmann_parallel_solver:
+ * `lattice_boltzmann_step` (src/lattice_boltzmann_method.py:191-228) with its boundary closures
+ * (src/boundary_conditions.py:78-348, bundles src/boundary_utils.py:9-205) and halo exchange
+ * (src/parallelization_utils.py:6-52). The reference is pure Python; what a maintainer binds is a ctypes
+ * stub. Plain C types only: the caller owns every host pointer, the context owns every
+ * device pointer. All functions return 0 on success or an LBM_ERR_* code; lbm_last_error() gives the text.
+ * One context per process and GPU; a context is not thread-safe. Calls are stream-ordered on the context's
+ * own streams and return without synchronising unless stated.
+ *
+ * Host array layout is the reference's: f[x][y][9] (C-contiguous, "AoS"), rho[x][y], u[x][y][2], float64.
+ * Device layout is SoA: S[i][x][y] with the reference's axis 1 ("y") as the coalesced axis, rows padded to
+ * 128 B. Device state is the POST-collision population set.
+ */
+#ifndef LBM_B200_H
+#define LBM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LBM_OK 0
+#define LBM_ERR_ARG 1      /* bad argument (AssertionError on the Python side, as the reference's asserts) */
+#define LBM_ERR_CUDA 2     /* CUDA runtime failure */
+#define LBM_ERR_STATE 3    /* call not valid in the context's current state */
+#define LBM_ERR_NOMEM 4
+#define LBM_ERR_TIMEOUT 5  /* a halo flag wait timed out (peer rank not stepping in lockstep) */
+
+const char *lbm_last_error(void);
+/* library version / build string (contains the compiled SM arch) */
+const char *lbm_version(void);
+/* number of visible CUDA devices, or a negative LBM_ERR_* */
+int lbm_device_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Stateless operators on host arrays. Replace, bit for bit:
+ *   lbm_equilibrium  <- equilibrium_distr_func   src/lattice_boltzmann_method.py:162-188
+ *   lbm_density      <- compute_density          src/lattice_boltzmann_method.py:93-105
+ *   lbm_velocity     <- compute_velocity_field   src/lattice_boltzmann_method.py:108-137
+ *   lbm_streaming    <- streaming                src/lattice_boltzmann_method.py:140-159
+ * n_cells = product of the leading dims. Each call copies in, runs one kernel, copies out, synchronises.
+ * ------------------------------------------------------------------------------------------------------- */
+int lbm_equilibrium(int device, int64_t n_cells, const double *rho, const double *u, double *f_out);
+int lbm_density(int device, int64_t n_cells, const double *f, double *rho_out);
+int lbm_velocity(int device, int64_t n_cells, const double *rho, const double *f, double *u_out);
+int lbm_streaming(int device, int nx, int ny, const double *f, double *f_out);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Boundary description. The reference composes Python closures that overwrite entries of f_post one after
+ * another (src/boundary_utils.py:52-53, 103-106, 164-203). Here the same effect is data: every lattice cell
+ * carries a one-byte KIND; a kind says, per population i, where f_post[i] of that cell comes from.
+ * ------------------------------------------------------------------------------------------------------- */
+enum {
+    LBM_RULE_PULL = 0,    /* f_post[i] = S[(x - c_i) mod n, i]           streaming,  lattice_boltzmann_method.py:153-157 */
+    LBM_RULE_BOUNCE = 1,  /* f_post[i] = S[x, opp(i)] - K[row][opp(i)]   rigid_wall / moving_wall / rigid_object,
+                                                                         boundary_conditions.py:108-109, 207-210, 153-163 */
+    LBM_RULE_CONST = 2,   /* f_post[i] = C[row][i]                       inlet,      boundary_conditions.py:250-251 */
+    LBM_RULE_OUTLET = 3   /* f_post[i] = f_prev[x-1, y, i]               outlet,     boundary_conditions.py:279-280 */
+};
+#define LBM_RULE(type, row) ((uint8_t)((type) | ((row) << 3)))   /* row: 0..31, row 0 of K is all zeros */
+
+enum {
+    LBM_CELL_OUTLET_SRC = 1,  /* this cell's f_post[3,6,7] is next step's f_prev[-2] (boundary_conditions.py:279-280) */
+    LBM_CELL_PBC_IN_SRC = 2,  /* row -2: owns S[0, y, (1,5,8)] of the next step (boundary_conditions.py:339-340) */
+    LBM_CELL_PBC_OUT_SRC = 4  /* row  1: owns S[-1, y, (3,6,7)]                 (boundary_conditions.py:343-344) */
+};
+
+typedef struct {
+    uint8_t rule[9];      /* LBM_RULE(type,row) per population */
+    uint8_t flags;        /* LBM_CELL_* */
+    uint16_t skip_store;  /* bit i set: S'[i] of this cell is written by a PBC source cell instead */
+} lbm_kind;
+
+typedef struct {
+    int n_kinds;               /* <= 256; kind 0 must be the all-PULL fluid cell */
+    const lbm_kind *kinds;
+    int n_k_rows;              /* <= 32 rows of 9 doubles; row 0 must be zeros */
+    const double *k_table;     /* K_d of moving_wall, indexed [row][d] (d = the population that hits the wall) */
+    int n_c_rows;              /* <= 32 rows of 9 doubles */
+    const double *c_table;     /* inlet constants, [row][i] */
+    double pbc_rho_in, pbc_rho_out;   /* p/c_s**2 of periodic_with_pressure_variations (boundary_conditions.py:306-309) */
+    const uint8_t *kind_map;   /* nx*ny bytes, reference index order [x][y]; NULL = all fluid */
+} lbm_bc_desc;
+
+/* Applies the closures' effect to host arrays (used when a boundary closure is CALLED directly, as the
+ * reference's tests/test_boundary_conditions.py does). f_post is updated in place; f_prev may be NULL when no
+ * OUTLET rule is present. PBC source flags are ignored here — use lbm_pbc_apply. */
+int lbm_bc_apply(int device, int nx, int ny, const lbm_bc_desc *bc, const double *f_pre, double *f_post,
+                 const double *f_prev);
+/* periodic_with_pressure_variations, x case, in place on f_pre (boundary_conditions.py:337-344). */
+int lbm_pbc_apply(int device, int nx, int ny, double rho_in, double rho_out, const double *rho, const double *u,
+                  double *f_pre);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Context: a device-resident lattice. nx, ny are the dims of the arrays the reference would hold on this
+ * rank (ghost ring included when ghost_x / ghost_y = 1, as experiments.py:618 allocates them).
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct lbm_ctx lbm_ctx;
+
+enum {
+    LBM_BC_AUTO = 0,      /* flag mask folded into the fused kernel below LBM_EDGE_THRESHOLD cells, edge kernel above */
+    LBM_BC_MASK = 1,      /* per-cell flag byte read by the fused kernel */
+    LBM_BC_EDGE = 2       /* mask-free periodic kernel over all cells + thin fix-up kernel over the non-fluid cells */
+};
+
+int lbm_create(int device, int nx, int ny, int ghost_x, int ghost_y, const lbm_bc_desc *bc /* may be NULL */,
+               lbm_ctx **out);
+int lbm_destroy(lbm_ctx *ctx);
+int lbm_set_bc_mode(lbm_ctx *ctx, int mode);
+/* bytes of device memory the context holds */
+int64_t lbm_device_bytes(const lbm_ctx *ctx);
+/* the cudaStream_t the step kernels are launched on (for CUDA-event timing by the caller) */
+void *lbm_stream(lbm_ctx *ctx);
+
+/* Loads the reference's state triple (lattice_boltzmann_method.py:191: f, density, velocity) and performs the
+ * first collision f + (feq(rho,u) - f)*omega with the GIVEN moments (:213-215). Synchronous. */
+int lbm_upload(lbm_ctx *ctx, const double *f, const double *rho, const double *u, double omega);
+/* Device-side initialisation without staging the lattice through the host (initial_values.py:38-123 are all
+ * separable): rho(x,y) = rho_x ? rho_x[x] : rho0;  u_x(x,y) = ux_y ? ux_y[y] : ux0;  u_y = uy0;
+ * f = feq(rho,u) (lattice_boltzmann_method.py:162-188), then the first collision as in lbm_upload. */
+int lbm_init_equilibrium(lbm_ctx *ctx, const double *rho_x, const double *ux_y, double rho0, double ux0,
+                         double uy0, double omega);
+
+/* Advances n_steps reference time steps (each: [collide ->] exchange -> stream -> BC -> moments -> collide).
+ * omega may differ from the previous call's (experiments.py:171-180 sweeps it): the speculative collision of
+ * the last step is then redone from the retained previous buffer. Asynchronous. */
+int lbm_step(lbm_ctx *ctx, double omega, int n_steps);
+/* Blocks until all queued work of the context is done; reports asynchronous errors. */
+int lbm_sync(lbm_ctx *ctx);
+/* Number of reference steps taken since the last upload / init. */
+int64_t lbm_time(const lbm_ctx *ctx);
+/* How many kernels this context has launched so far (bench.py's gpu_launches). */
+int64_t lbm_launch_count(const lbm_ctx *ctx);
+
+/* Copies the reference-layout state (f_post, density, velocity of lattice_boltzmann_method.py:225-228) of
+ * the current time to host arrays; any pointer may be NULL. Whole arrays, ghost ring included. Synchronous. */
+int lbm_materialize(lbm_ctx *ctx, double *f, double *rho, double *u);
+/* Same for the sub-rectangle [x0,x1) x [y0,y1) (row-major, packed). */
+int lbm_materialize_region(lbm_ctx *ctx, int x0, int x1, int y0, int y1, double *f, double *rho, double *u);
+
+/* Probe: records (u_x, u_y) at one cell after every step into a device ring (experiments.py:703-704).
+ * lbm_probe_read copies the samples of steps [t0, t0+n) — at most `capacity` behind lbm_time(). Synchronous. */
+int lbm_probe_config(lbm_ctx *ctx, int x, int y, int capacity);
+int lbm_probe_read(lbm_ctx *ctx, int64_t t0, int n, double *uxuy);
+/* Whole-field extrema of the current state (experiments.py:181-193): out = {min rho, max rho, min u, max u}
+ * over the cells [x0,x1) x [y0,y1); u extrema are over both components, as np.amin(velocity). Synchronous. */
+int lbm_minmax(lbm_ctx *ctx, int x0, int x1, int y0, int y1, double out[4]);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Halo exchange (replaces communication(), src/parallelization_utils.py:6-52). Ghost cells of a neighbour
+ * are written DIRECTLY by the kernel that computes the edge cells (peer stores over NVLink through a CUDA-IPC
+ * mapping), ordered by step flags in peer memory; there is no separate copy or pack step.
+ * Neighbour slot index = (dx+1)*3 + (dy+1), dx,dy in {-1,0,1}, (0,0) unused.
+ * ------------------------------------------------------------------------------------------------------- */
+#define LBM_IPC_HANDLE_BYTES 64
+typedef struct {
+    uint8_t mem_handle[LBM_IPC_HANDLE_BYTES];  /* cudaIpcMemHandle_t of the context's arena */
+    int32_t device;
+    int32_t nx, ny, pitch;
+    int64_t pid;                               /* same pid => same process: use the pointer directly */
+    uint64_t arena_ptr;                        /* only meaningful within that process */
+    int64_t arena_bytes;
+} lbm_halo_export;
+
+int lbm_halo_export_handle(lbm_ctx *ctx, lbm_halo_export *out);
+/* slot's neighbour is the context described by `peer` (may be this context itself: self-periodic wrap). */
+int lbm_halo_connect(lbm_ctx *ctx, int slot, const lbm_halo_export *peer);
+/* Call once after every rank has connected all its neighbours (and after a process-group barrier). */
+int lbm_halo_finalize(lbm_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LBM_B200_H */

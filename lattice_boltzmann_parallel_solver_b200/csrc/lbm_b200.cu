@@ -1,0 +1,1394 @@
+// lbm_b200.cu — B200 (sm_100a) implementation of include/lbm_b200.h.
+//
+// State on the device is the POST-collision population set S[i][x][y] (SoA fp64, rows padded to 128 B, two
+// buffers A/B). One fused kernel maps S_t -> S_{t+1} per reference time step:
+//     pull-stream (lattice_boltzmann_method.py:153-157) -> boundary rules (boundary_conditions.py) ->
+//     moments (:93-137) -> equilibrium (:162-188) -> BGK collide (:215) -> store [+ ghost stores to neighbours]
+// reading every population once and writing it once (144 B per cell update). See DESIGN.md.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <unistd.h>
+
+#include "../../include/lbm_b200.h"
+#include "lbm_device.cuh"
+
+using namespace lbm;
+
+// -------------------------------------------------------------------------------------------------------
+// errors
+// -------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(LBM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char *lbm_last_error(void) { return g_err.c_str(); }
+extern "C" const char *lbm_version(void) { return "lbm_b200 0.1 (sm_100a, fp64, pull/post-collision state)"; }
+extern "C" int lbm_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// -------------------------------------------------------------------------------------------------------
+// kernel parameter blocks
+// -------------------------------------------------------------------------------------------------------
+struct HaloTarget {
+    double *base;      // population-0 plane of the neighbour's DESTINATION buffer (this step's parity); null = none
+    long long plane;   // its plane stride (doubles)
+    int nx, ny, pitch;
+};
+
+struct StepParams {
+    const double *src;
+    double *dst;
+    long long plane;   // NX * pitch
+    int pitch, NX, NY;
+    int gx, gy;
+    // rows handled by this launch: [row0a, row0a+na) then [row0b, ...)
+    int row0a, na, row0b;
+    int bpr;           // blocks per row
+    int y0, y1;        // columns handled: [y0, y1)
+    double omega;
+    const uint8_t *kind_map;   // [x*pitch + y] or null
+    const lbm_kind *kinds;
+    const double *ktab, *ctab;
+    const double *out_cur;     // outlet side buffer read by OUTLET rules  [3][pitch]
+    double *out_next;          // written by OUTLET_SRC cells
+    double rho_in, rho_out;
+    int px, py;
+    double *probe_slot;
+    // FINAL (materialize) outputs, packed over [ox0,ox1) x [oy0,oy1)
+    double *o_f, *o_rho, *o_u;
+    int ox0, oy0, ow;          // ow = oy1 - oy0
+    // halo
+    HaloTarget halo[9];
+    // fix-up list
+    const int2 *cells;
+    int n_cells;
+    // cross-GPU step flags
+    volatile unsigned *flag_in;     // [9] in my arena: neighbour slot s finished writing my ghosts of step value
+    unsigned *flag_out[9];          // neighbour's flag_in[opposite slot] (peer memory) or null
+    unsigned wait_value, signal_value;
+    unsigned *done_counter;         // last-block-done counter
+    unsigned *err_flag;
+    int n_blocks;
+};
+
+// -------------------------------------------------------------------------------------------------------
+// per-cell pieces shared by all kernels
+// -------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double ldS(const double *p) { return __ldcg(p); }   // L2-coherent (peer-written ghosts)
+
+// f_post of one fluid cell: nine pulls with periodic wrap over the local array (np.roll semantics)
+__device__ __forceinline__ void pull_fluid(const StepParams &P, int x, int y, double (&f)[9])
+{
+    const int xm = x == 0 ? P.NX - 1 : x - 1, xp = x == P.NX - 1 ? 0 : x + 1;
+    const int ym = y == 0 ? P.NY - 1 : y - 1, yp = y == P.NY - 1 ? 0 : y + 1;
+    const double *r0 = P.src + (long long)x * P.pitch;
+    const double *rm = P.src + (long long)xm * P.pitch;
+    const double *rp = P.src + (long long)xp * P.pitch;
+    const long long pl = P.plane;
+    f[0] = ldS(r0 + y);
+    f[1] = ldS(rm + pl + y);
+    f[2] = ldS(r0 + 2 * pl + ym);
+    f[3] = ldS(rp + 3 * pl + y);
+    f[4] = ldS(r0 + 4 * pl + yp);
+    f[5] = ldS(rm + 5 * pl + ym);
+    f[6] = ldS(rp + 6 * pl + ym);
+    f[7] = ldS(rp + 7 * pl + yp);
+    f[8] = ldS(rm + 8 * pl + yp);
+}
+
+// f_post of a non-fluid cell, population by population (rule table of include/lbm_b200.h)
+__device__ __noinline__ void pull_rules(const StepParams &P, const lbm_kind &k, int x, int y, double (&f)[9])
+{
+    const long long pl = P.plane;
+#pragma unroll 1
+    for (int i = 0; i < 9; i++) {
+        const int r = k.rule[i], type = r & 7, row = r >> 3;
+        double v;
+        if (type == LBM_RULE_PULL) {
+            int xs = x - kCx[i], ys = y - kCy[i];
+            xs = xs < 0 ? P.NX - 1 : (xs >= P.NX ? 0 : xs);
+            ys = ys < 0 ? P.NY - 1 : (ys >= P.NY ? 0 : ys);
+            v = ldS(P.src + i * pl + (long long)xs * P.pitch + ys);
+        } else if (type == LBM_RULE_BOUNCE) {
+            const int d = kOpp[i];
+            v = ldS(P.src + d * pl + (long long)x * P.pitch + y);
+            if (row) v = sub(v, P.ktab[row * 9 + d]);
+        } else if (type == LBM_RULE_CONST) {
+            v = P.ctab[row * 9 + i];
+        } else {  // LBM_RULE_OUTLET: i in (3,6,7) -> slot 0,1,2
+            const int slot = i == 3 ? 0 : (i == 6 ? 1 : 2);
+            v = P.out_cur[slot * P.pitch + y];
+        }
+        f[i] = v;
+    }
+}
+
+// Everything after the collision: stores of S' (own cell, PBC-owned virtual cells, neighbours' ghosts)
+__device__ __forceinline__ void store_cell(const StepParams &P, int x, int y, const double (&s)[9], unsigned skip)
+{
+    double *d = P.dst + (long long)x * P.pitch + y;
+    const long long pl = P.plane;
+    if (skip == 0) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) __stcg(d + i * pl, s[i]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 9; i++)
+            if (!((skip >> i) & 1)) __stcg(d + i * pl, s[i]);
+    }
+}
+
+// periodic_with_pressure_variations (boundary_conditions.py:337-344): the cell on row -2 (resp. 1) produces the
+// pre-streaming populations of the virtual node on row 0 (resp. -1) for the NEXT step:
+//   feq_d(rho_b, u) + (f_pre_d - feq_d(rho, u)),  f_pre_d = the value just collided (s), u/rho this cell's moments
+__device__ __noinline__ void store_pbc(const StepParams &P, unsigned flags, int y, const double (&s)[9],
+                                       const double (&p)[9], const double (&e)[9])
+{
+    const long long pl = P.plane;
+    if (flags & LBM_CELL_PBC_IN_SRC) {
+        const double w1 = mul(LBM_W1, P.rho_in), w5 = mul(LBM_W5, P.rho_in);
+        double *d = P.dst + y;  // row 0
+        __stcg(d + 1 * pl, add(mul(w1, p[1]), sub(s[1], e[1])));
+        __stcg(d + 5 * pl, add(mul(w5, p[5]), sub(s[5], e[5])));
+        __stcg(d + 8 * pl, add(mul(w5, p[8]), sub(s[8], e[8])));
+    }
+    if (flags & LBM_CELL_PBC_OUT_SRC) {
+        const double w1 = mul(LBM_W1, P.rho_out), w5 = mul(LBM_W5, P.rho_out);
+        double *d = P.dst + (long long)(P.NX - 1) * P.pitch + y;  // row -1
+        __stcg(d + 3 * pl, add(mul(w1, p[3]), sub(s[3], e[3])));
+        __stcg(d + 6 * pl, add(mul(w5, p[6]), sub(s[6], e[6])));
+        __stcg(d + 7 * pl, add(mul(w5, p[7]), sub(s[7], e[7])));
+    }
+}
+
+// communication() (parallelization_utils.py:34-49) without the copy: an interior cell on the edge of the block
+// also writes its nine post-collision populations into the ghost cell(s) of the neighbour(s) that mirror it.
+__device__ __noinline__ void store_halo(const StepParams &P, int x, int y, const double (&s)[9])
+{
+    const int ex_lo = (P.gx && x == P.gx), ex_hi = (P.gx && x == P.NX - 1 - P.gx);
+    const int ey_lo = (P.gy && y == P.gy), ey_hi = (P.gy && y == P.NY - 1 - P.gy);
+    if (!(ex_lo | ex_hi | ey_lo | ey_hi)) return;
+#pragma unroll 1
+    for (int ix = 0; ix < 3; ix++) {          // ix: 0 -> neighbour at dx=-1, 1 -> same, 2 -> dx=+1
+        if ((ix == 0 && !ex_lo) || (ix == 2 && !ex_hi)) continue;
+#pragma unroll 1
+        for (int iy = 0; iy < 3; iy++) {
+            if ((iy == 0 && !ey_lo) || (iy == 2 && !ey_hi)) continue;
+            if (ix == 1 && iy == 1) continue;
+            const HaloTarget &T = P.halo[ix * 3 + iy];
+            if (!T.base) continue;
+            // my first interior row is the low neighbour's high ghost row, and so on
+            const int tx = ix == 0 ? T.nx - 1 : (ix == 2 ? 0 : x);
+            const int ty = iy == 0 ? T.ny - 1 : (iy == 2 ? 0 : y);
+            double *d = T.base + (long long)tx * T.pitch + ty;
+#pragma unroll
+            for (int i = 0; i < 9; i++) d[i * T.plane] = s[i];
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------
+// cross-GPU ordering: wait until every remote neighbour has published `wait_value`, publish `signal_value`
+// once the whole grid has finished its (peer) stores.
+// -------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void halo_wait(const StepParams &P)
+{
+    if (P.wait_value == 0) return;
+    if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        for (int s = 0; s < 9; s++) {
+            if (!P.flag_out[s]) continue;   // not a remote neighbour
+            while ((int)(P.flag_in[s] - P.wait_value) < 0) {
+                if (clock64() - t0 > 20000000000LL) {   // ~10 s: a peer is not stepping in lockstep
+                    atomicExch(P.err_flag, 1u);
+                    break;
+                }
+                __nanosleep(200);
+            }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void halo_signal(const StepParams &P)
+{
+    if (P.signal_value == 0) return;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned done = atomicAdd(P.done_counter, 1u);
+        if (done == (unsigned)P.n_blocks - 1) {
+            *P.done_counter = 0;
+            __threadfence_system();
+            for (int s = 0; s < 9; s++)
+                if (P.flag_out[s]) *(volatile unsigned *)P.flag_out[s] = P.signal_value;
+            __threadfence_system();
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------
+// the fused step kernel
+//   MASK : read the per-cell kind byte (boundary rules folded into the kernel)
+//   HALO : edge cells also store into neighbours' ghost cells; flags ordering
+//   FINAL: stop after the moments and write reference-layout f_post / rho / u (materialize)
+//   LIST : cells come from a compact list (edge fix-up kernel) instead of a row range
+// -------------------------------------------------------------------------------------------------------
+template <bool MASK, bool HALO, bool FINAL, bool LIST>
+__global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepParams P)
+{
+    if (HALO && !FINAL) halo_wait(P);
+    int x, y;
+    bool active = true;
+    if (LIST) {
+        const int c = blockIdx.x * blockDim.x + threadIdx.x;
+        active = c < P.n_cells;
+        const int2 xy = active ? P.cells[c] : make_int2(0, 0);
+        x = xy.x;
+        y = xy.y;
+    } else {
+        const int rb = blockIdx.x / P.bpr, cb = blockIdx.x - rb * P.bpr;
+        x = rb < P.na ? P.row0a + rb : P.row0b + (rb - P.na);
+        y = P.y0 + cb * blockDim.x + threadIdx.x;
+        active = y < P.y1;
+    }
+    if (active) {
+        double f[9];
+        unsigned flags = 0, skip = 0;
+        bool fluid = true;
+        if (MASK || LIST) {
+            const unsigned kind = P.kind_map[(long long)x * P.pitch + y];
+            if (kind != 0) {
+                fluid = false;
+                const lbm_kind k = P.kinds[kind];
+                flags = k.flags;
+                skip = k.skip_store;
+                pull_rules(P, k, x, y, f);
+            }
+        }
+        if (fluid) pull_fluid(P, x, y, f);
+
+        double rho, ux, uy;
+        moments(f, rho, ux, uy);
+
+        if (FINAL) {
+            const long long o = (long long)(x - P.ox0) * P.ow + (y - P.oy0);
+            if (P.o_f) {
+#pragma unroll
+                for (int i = 0; i < 9; i++) P.o_f[o * 9 + i] = f[i];
+            }
+            if (P.o_rho) P.o_rho[o] = rho;
+            if (P.o_u) {
+                P.o_u[o * 2] = ux;
+                P.o_u[o * 2 + 1] = uy;
+            }
+        } else {
+            if (P.probe_slot && x == P.px && y == P.py) {
+                P.probe_slot[0] = ux;
+                P.probe_slot[1] = uy;
+            }
+            double p[9], e[9], s[9];
+            eq_poly(ux, uy, p);
+            eq_from_poly(rho, p, e);
+            collide(f, e, P.omega, s);
+            if ((MASK || LIST) && (flags & LBM_CELL_OUTLET_SRC)) {
+                P.out_next[0 * P.pitch + y] = f[3];
+                P.out_next[1 * P.pitch + y] = f[6];
+                P.out_next[2 * P.pitch + y] = f[7];
+            }
+            store_cell(P, x, y, s, skip);
+            if ((MASK || LIST) && (flags & (LBM_CELL_PBC_IN_SRC | LBM_CELL_PBC_OUT_SRC))) store_pbc(P, flags, y, s, p, e);
+            if (HALO) store_halo(P, x, y, s);
+        }
+    }
+    if (HALO && !FINAL) halo_signal(P);
+}
+
+// -------------------------------------------------------------------------------------------------------
+// first collision of an uploaded / initialised state: S_0 = f + (feq(rho,u) - f)*omega with the GIVEN moments
+// (lattice_boltzmann_method.py:213-215). Input is either reference-layout staging (rows [x0, x0+nrows)) or the
+// separable initial fields of initial_values.py.
+// -------------------------------------------------------------------------------------------------------
+struct InitParams {
+    StepParams S;
+    const double *in_f, *in_rho, *in_u;   // AoS staging of rows [x0, x0+nrows), or null
+    const double *rho_x, *ux_y;           // separable profiles (device), may be null
+    double rho0, ux0, uy0;
+    int x0, nrows;
+};
+
+template <bool HALO>
+__global__ void __launch_bounds__(256) k_first_collide(const __grid_constant__ InitParams Q)
+{
+    const StepParams &P = Q.S;
+    const int rb = blockIdx.x / P.bpr, cb = blockIdx.x - rb * P.bpr;
+    const int x = Q.x0 + rb, y = cb * blockDim.x + threadIdx.x;
+    if (y >= P.NY) return;
+    double f[9], rho, ux, uy, p[9], e[9], s[9];
+    if (Q.in_f) {
+        const long long c = (long long)rb * P.NY + y;
+#pragma unroll
+        for (int i = 0; i < 9; i++) f[i] = Q.in_f[c * 9 + i];
+        rho = Q.in_rho[c];
+        ux = Q.in_u[2 * c];
+        uy = Q.in_u[2 * c + 1];
+        eq_poly(ux, uy, p);
+        eq_from_poly(rho, p, e);
+    } else {
+        rho = Q.rho_x ? Q.rho_x[x] : Q.rho0;
+        ux = Q.ux_y ? Q.ux_y[y] : Q.ux0;
+        uy = Q.uy0;
+        eq_poly(ux, uy, p);
+        eq_from_poly(rho, p, e);
+#pragma unroll
+        for (int i = 0; i < 9; i++) f[i] = e[i];   // f = equilibrium_distr_func(density, velocity), experiments.py:122
+    }
+    collide(f, e, P.omega, s);
+    unsigned flags = 0, skip = 0;
+    if (P.kind_map) {
+        const unsigned kind = P.kind_map[(long long)x * P.pitch + y];
+        if (kind) {
+            flags = P.kinds[kind].flags;
+            skip = P.kinds[kind].skip_store;
+        }
+    }
+    if (flags & LBM_CELL_OUTLET_SRC) {   // f_previous of the first step is the uploaded f itself
+        P.out_next[0 * P.pitch + y] = f[3];
+        P.out_next[1 * P.pitch + y] = f[6];
+        P.out_next[2 * P.pitch + y] = f[7];
+    }
+    // ghost cells are owned by the neighbour that mirrors them (communicate() overwrites them before streaming)
+    const bool ghost = (P.gx && (x == 0 || x == P.NX - 1)) || (P.gy && (y == 0 || y == P.NY - 1));
+    if (!ghost) {
+        store_cell(P, x, y, s, skip);
+        if (flags & (LBM_CELL_PBC_IN_SRC | LBM_CELL_PBC_OUT_SRC)) store_pbc(P, flags, y, s, p, e);
+        if (HALO) store_halo(P, x, y, s);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------
+// stateless operators on reference-layout arrays
+// -------------------------------------------------------------------------------------------------------
+__global__ void k_equilibrium(long long n, const double *rho, const double *u, double *out)
+{
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    double p[9], e[9];
+    eq_poly(u[2 * c], u[2 * c + 1], p);
+    eq_from_poly(rho[c], p, e);
+#pragma unroll
+    for (int i = 0; i < 9; i++) out[9 * c + i] = e[i];
+}
+
+__global__ void k_moments(long long n, const double *f, const double *rho_in, double *rho_out, double *u_out)
+{
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    double g[9], rho, ux, uy;
+#pragma unroll
+    for (int i = 0; i < 9; i++) g[i] = f[9 * c + i];
+    moments(g, rho, ux, uy);
+    if (rho_out) rho_out[c] = rho;
+    if (u_out) {
+        if (rho_in) {   // compute_velocity_field(density, f) divides by the GIVEN density
+            const double r = rho_in[c];
+            const double jx = sub(add(add(g[1], g[5]), g[8]), add(add(g[3], g[6]), g[7]));
+            const double jy = sub(add(add(g[2], g[5]), g[6]), add(add(g[4], g[7]), g[8]));
+            ux = r != 0.0 ? __ddiv_rn(jx, r) : 0.0;
+            uy = r != 0.0 ? __ddiv_rn(jy, r) : 0.0;
+        }
+        u_out[2 * c] = ux;
+        u_out[2 * c + 1] = uy;
+    }
+}
+
+__global__ void k_streaming_aos(int nx, int ny, const double *f, double *out)
+{
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= (long long)nx * ny) return;
+    const int x = (int)(c / ny), y = (int)(c - (long long)x * ny);
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        int xs = x - kCx[i], ys = y - kCy[i];
+        xs = xs < 0 ? nx - 1 : (xs >= nx ? 0 : xs);
+        ys = ys < 0 ? ny - 1 : (ys >= ny ? 0 : ys);
+        out[9 * c + i] = f[((long long)xs * ny + ys) * 9 + i];
+    }
+}
+
+__global__ void k_bc_apply_aos(int nx, int ny, const uint8_t *kind_map, const lbm_kind *kinds, const double *ktab,
+                               const double *ctab, const double *f_pre, double *f_post, const double *f_prev)
+{
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= (long long)nx * ny) return;
+    const unsigned kind = kind_map[c];
+    if (!kind) return;
+    const lbm_kind k = kinds[kind];
+    const int x = (int)(c / ny);
+    for (int i = 0; i < 9; i++) {
+        const int type = k.rule[i] & 7, row = k.rule[i] >> 3;
+        if (type == LBM_RULE_BOUNCE) {
+            const int d = kOpp[i];
+            double v = f_pre[9 * c + d];
+            if (row) v = sub(v, ktab[row * 9 + d]);
+            f_post[9 * c + i] = v;
+        } else if (type == LBM_RULE_CONST) {
+            f_post[9 * c + i] = ctab[row * 9 + i];
+        } else if (type == LBM_RULE_OUTLET) {
+            if (x > 0) f_post[9 * c + i] = f_prev[9 * (c - ny) + i];
+        }
+    }
+}
+
+__global__ void k_pbc_apply_aos(int nx, int ny, double rho_in, double rho_out, const double *rho, const double *u,
+                                double *f_pre)
+{
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= ny) return;
+    double p[9], e[9];
+    {   // inflow: row 0 from row -2, populations 1,5,8
+        const long long s = (long long)(nx - 2) * ny + y, d = y;
+        eq_poly(u[2 * s], u[2 * s + 1], p);
+        eq_from_poly(rho[s], p, e);
+        const double w1 = mul(LBM_W1, rho_in), w5 = mul(LBM_W5, rho_in);
+        const double v1 = add(mul(w1, p[1]), sub(f_pre[9 * s + 1], e[1]));
+        const double v5 = add(mul(w5, p[5]), sub(f_pre[9 * s + 5], e[5]));
+        const double v8 = add(mul(w5, p[8]), sub(f_pre[9 * s + 8], e[8]));
+        f_pre[9 * d + 1] = v1;
+        f_pre[9 * d + 5] = v5;
+        f_pre[9 * d + 8] = v8;
+    }
+    __syncthreads();   // nx == 3 would alias; rows are distinct otherwise and each thread owns its y
+    {   // outflow: row -1 from row 1, populations 3,6,7
+        const long long s = (long long)1 * ny + y, d = (long long)(nx - 1) * ny + y;
+        eq_poly(u[2 * s], u[2 * s + 1], p);
+        eq_from_poly(rho[s], p, e);
+        const double w1 = mul(LBM_W1, rho_out), w5 = mul(LBM_W5, rho_out);
+        f_pre[9 * d + 3] = add(mul(w1, p[3]), sub(f_pre[9 * s + 3], e[3]));
+        f_pre[9 * d + 6] = add(mul(w5, p[6]), sub(f_pre[9 * s + 6], e[6]));
+        f_pre[9 * d + 7] = add(mul(w5, p[7]), sub(f_pre[9 * s + 7], e[7]));
+    }
+}
+
+// min/max over packed rho / u staging (order-preserving integer image of a double)
+__device__ __forceinline__ long long ord(double v)
+{
+    long long b = __double_as_longlong(v);
+    return b < 0 ? (long long)(0x8000000000000000ULL - (unsigned long long)b) : b;
+}
+__host__ __device__ inline double unord(long long o)
+{
+    unsigned long long b = o < 0 ? (0x8000000000000000ULL - (unsigned long long)o) : (unsigned long long)o;
+    double v;
+    memcpy(&v, &b, 8);
+    return v;
+}
+
+__global__ void k_minmax(long long n, const double *rho, const double *u, long long *acc /* [4] */)
+{
+    long long mn_r = 0x7fffffffffffffffLL, mx_r = -0x7fffffffffffffffLL - 1, mn_u = mn_r, mx_u = mx_r;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
+        const long long r = ord(rho[c]), a = ord(u[2 * c]), b = ord(u[2 * c + 1]);
+        mn_r = min(mn_r, r);
+        mx_r = max(mx_r, r);
+        mn_u = min(mn_u, min(a, b));
+        mx_u = max(mx_u, max(a, b));
+    }
+    for (int o = 16; o; o >>= 1) {
+        mn_r = min(mn_r, __shfl_xor_sync(0xffffffffu, mn_r, o));
+        mx_r = max(mx_r, __shfl_xor_sync(0xffffffffu, mx_r, o));
+        mn_u = min(mn_u, __shfl_xor_sync(0xffffffffu, mn_u, o));
+        mx_u = max(mx_u, __shfl_xor_sync(0xffffffffu, mx_u, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(acc + 0, mn_r);
+        atomicMax(acc + 1, mx_r);
+        atomicMin(acc + 2, mn_u);
+        atomicMax(acc + 3, mx_u);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------------------
+struct Peer {
+    bool connected = false, remote = false;
+    void *mapped = nullptr;     // cudaIpcOpenMemHandle result (remote only)
+    char *arena = nullptr;      // base of the neighbour's arena in this process' address space
+    int nx = 0, ny = 0, pitch = 0;
+};
+
+struct lbm_ctx {
+    int device = 0;
+    int NX = 0, NY = 0, pitch = 0, gx = 0, gy = 0;
+    long long plane = 0;
+    // arena layout (one allocation so that one IPC handle exports everything a neighbour needs)
+    char *arena = nullptr;
+    size_t arena_bytes = 0;
+    size_t off_S[2] = {0, 0}, off_flags = 0;
+    double *S[2] = {nullptr, nullptr};
+    unsigned *flags_in = nullptr;       // [9] inside the arena
+    // other device memory
+    uint8_t *kind_map = nullptr;
+    lbm_kind *kinds = nullptr;
+    double *ktab = nullptr, *ctab = nullptr;
+    double *outbuf[2] = {nullptr, nullptr};
+    int2 *cells = nullptr;
+    int n_cells = 0;
+    bool has_bc = false;
+    double rho_in = 0, rho_out = 0;
+    int bc_mode = LBM_BC_AUTO;
+    unsigned *done_counter = nullptr, *err_flag = nullptr;
+    // staging for upload / materialize (reference layout, a chunk of rows)
+    double *stage_f = nullptr, *stage_rho = nullptr, *stage_u = nullptr;
+    long long stage_cells = 0;
+    long long *mm_acc = nullptr;
+    // probe ring
+    int px = -1, py = -1, probe_cap = 0;
+    double *probe = nullptr;
+    // state
+    int cur = 0;              // S[cur] = S_t
+    bool loaded = false;
+    long long t = 0;          // reference steps since upload
+    double omega = 0;
+    long long launches = 0;
+    unsigned halo_epoch = 0;  // value published after the kernel that produced S_t
+    // halo
+    Peer peer[9];
+    bool halo_ready = false, any_remote = false;
+    cudaStream_t stream = nullptr, stream_edge = nullptr;
+    cudaEvent_t ev_main = nullptr, ev_edge = nullptr;
+};
+
+static const long long kEdgeThreshold = 1 << 20;   // cells; LBM_BC_AUTO switches to the edge kernel above this
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int set_device(int device)
+{
+    CK(cudaSetDevice(device));
+    return LBM_OK;
+}
+
+// ---- stateless ops -------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf()
+    {
+        if (p) cudaFree(p);
+    }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 1); }
+    template <class T>
+    T *as()
+    {
+        return (T *)p;
+    }
+};
+
+extern "C" int lbm_equilibrium(int device, int64_t n, const double *rho, const double *u, double *f_out)
+{
+    if (n < 0 || !rho || !u || !f_out) return fail(LBM_ERR_ARG, "lbm_equilibrium: null pointer or negative size");
+    if (n == 0) return LBM_OK;
+    if (int rc = set_device(device)) return rc;
+    DevBuf dr, du, df;
+    CK(dr.alloc(n * 8));
+    CK(du.alloc(n * 16));
+    CK(df.alloc(n * 72));
+    CK(cudaMemcpy(dr.p, rho, n * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(du.p, u, n * 16, cudaMemcpyHostToDevice));
+    k_equilibrium<<<(unsigned)((n + 255) / 256), 256>>>(n, dr.as<double>(), du.as<double>(), df.as<double>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(f_out, df.p, n * 72, cudaMemcpyDeviceToHost));
+    return LBM_OK;
+}
+
+static int moments_op(int device, int64_t n, const double *rho_in, const double *f, double *rho_out, double *u_out)
+{
+    if (n == 0) return LBM_OK;
+    if (int rc = set_device(device)) return rc;
+    DevBuf df, dri, dro, du;
+    CK(df.alloc(n * 72));
+    CK(cudaMemcpy(df.p, f, n * 72, cudaMemcpyHostToDevice));
+    if (rho_in) {
+        CK(dri.alloc(n * 8));
+        CK(cudaMemcpy(dri.p, rho_in, n * 8, cudaMemcpyHostToDevice));
+    }
+    if (rho_out) CK(dro.alloc(n * 8));
+    if (u_out) CK(du.alloc(n * 16));
+    k_moments<<<(unsigned)((n + 255) / 256), 256>>>(n, df.as<double>(), rho_in ? dri.as<double>() : nullptr,
+                                                    rho_out ? dro.as<double>() : nullptr, u_out ? du.as<double>() : nullptr);
+    CK(cudaGetLastError());
+    if (rho_out) CK(cudaMemcpy(rho_out, dro.p, n * 8, cudaMemcpyDeviceToHost));
+    if (u_out) CK(cudaMemcpy(u_out, du.p, n * 16, cudaMemcpyDeviceToHost));
+    return LBM_OK;
+}
+
+extern "C" int lbm_density(int device, int64_t n, const double *f, double *rho_out)
+{
+    if (n < 0 || !f || !rho_out) return fail(LBM_ERR_ARG, "lbm_density: null pointer or negative size");
+    return moments_op(device, n, nullptr, f, rho_out, nullptr);
+}
+
+extern "C" int lbm_velocity(int device, int64_t n, const double *rho, const double *f, double *u_out)
+{
+    if (n < 0 || !rho || !f || !u_out) return fail(LBM_ERR_ARG, "lbm_velocity: null pointer or negative size");
+    return moments_op(device, n, rho, f, nullptr, u_out);
+}
+
+extern "C" int lbm_streaming(int device, int nx, int ny, const double *f, double *f_out)
+{
+    if (nx <= 0 || ny <= 0 || !f || !f_out) return fail(LBM_ERR_ARG, "lbm_streaming: bad shape or null pointer");
+    if (int rc = set_device(device)) return rc;
+    const long long n = (long long)nx * ny;
+    DevBuf a, b;
+    CK(a.alloc(n * 72));
+    CK(b.alloc(n * 72));
+    CK(cudaMemcpy(a.p, f, n * 72, cudaMemcpyHostToDevice));
+    k_streaming_aos<<<(unsigned)((n + 255) / 256), 256>>>(nx, ny, a.as<double>(), b.as<double>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(f_out, b.p, n * 72, cudaMemcpyDeviceToHost));
+    return LBM_OK;
+}
+
+static int check_bc(const lbm_bc_desc *bc)
+{
+    if (bc->n_kinds < 1 || bc->n_kinds > 256 || !bc->kinds) return fail(LBM_ERR_ARG, "bc: n_kinds must be 1..256");
+    if (bc->n_k_rows < 1 || bc->n_k_rows > 32 || !bc->k_table) return fail(LBM_ERR_ARG, "bc: n_k_rows must be 1..32");
+    if (bc->n_c_rows < 0 || bc->n_c_rows > 32) return fail(LBM_ERR_ARG, "bc: n_c_rows must be 0..32");
+    for (int i = 0; i < 9; i++) {
+        if (bc->kinds[0].rule[i] != 0) return fail(LBM_ERR_ARG, "bc: kind 0 must be the all-PULL fluid cell");
+        if (bc->k_table[i] != 0.0) return fail(LBM_ERR_ARG, "bc: row 0 of k_table must be zero");
+    }
+    if (bc->kinds[0].flags || bc->kinds[0].skip_store) return fail(LBM_ERR_ARG, "bc: kind 0 must carry no flags");
+    for (int k = 0; k < bc->n_kinds; k++)
+        for (int i = 0; i < 9; i++) {
+            const int type = bc->kinds[k].rule[i] & 7, row = bc->kinds[k].rule[i] >> 3;
+            if (type > LBM_RULE_OUTLET) return fail(LBM_ERR_ARG, "bc: unknown rule type %d", type);
+            if (type == LBM_RULE_BOUNCE && row >= bc->n_k_rows) return fail(LBM_ERR_ARG, "bc: k_table row out of range");
+            if (type == LBM_RULE_CONST && row >= bc->n_c_rows) return fail(LBM_ERR_ARG, "bc: c_table row out of range");
+            if (type == LBM_RULE_OUTLET && !(i == 3 || i == 6 || i == 7))
+                return fail(LBM_ERR_ARG, "bc: OUTLET rule only exists for populations 3, 6, 7");
+        }
+    return LBM_OK;
+}
+
+extern "C" int lbm_bc_apply(int device, int nx, int ny, const lbm_bc_desc *bc, const double *f_pre, double *f_post,
+                            const double *f_prev)
+{
+    if (nx <= 0 || ny <= 0 || !bc || !f_pre || !f_post || !bc->kind_map) return fail(LBM_ERR_ARG, "lbm_bc_apply: bad argument");
+    if (int rc = check_bc(bc)) return rc;
+    if (int rc = set_device(device)) return rc;
+    const long long n = (long long)nx * ny;
+    DevBuf dm, dk, dkt, dct, a, b, c;
+    CK(dm.alloc(n));
+    CK(dk.alloc(bc->n_kinds * sizeof(lbm_kind)));
+    CK(dkt.alloc(bc->n_k_rows * 72));
+    CK(dct.alloc(std::max(bc->n_c_rows, 1) * 72));
+    CK(a.alloc(n * 72));
+    CK(b.alloc(n * 72));
+    CK(cudaMemcpy(dm.p, bc->kind_map, n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dk.p, bc->kinds, bc->n_kinds * sizeof(lbm_kind), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dkt.p, bc->k_table, bc->n_k_rows * 72, cudaMemcpyHostToDevice));
+    if (bc->n_c_rows) CK(cudaMemcpy(dct.p, bc->c_table, bc->n_c_rows * 72, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(a.p, f_pre, n * 72, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b.p, f_post, n * 72, cudaMemcpyHostToDevice));
+    if (f_prev) {
+        CK(c.alloc(n * 72));
+        CK(cudaMemcpy(c.p, f_prev, n * 72, cudaMemcpyHostToDevice));
+    } else {
+        for (int k = 0; k < bc->n_kinds; k++)
+            for (int i = 0; i < 9; i++)
+                if ((bc->kinds[k].rule[i] & 7) == LBM_RULE_OUTLET) return fail(LBM_ERR_ARG, "lbm_bc_apply: OUTLET rule needs f_prev");
+    }
+    k_bc_apply_aos<<<(unsigned)((n + 255) / 256), 256>>>(nx, ny, dm.as<uint8_t>(), dk.as<lbm_kind>(), dkt.as<double>(),
+                                                         dct.as<double>(), a.as<double>(), b.as<double>(), c.as<double>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(f_post, b.p, n * 72, cudaMemcpyDeviceToHost));
+    return LBM_OK;
+}
+
+extern "C" int lbm_pbc_apply(int device, int nx, int ny, double rho_in, double rho_out, const double *rho, const double *u,
+                             double *f_pre)
+{
+    if (nx < 4 || ny <= 0 || !rho || !u || !f_pre) return fail(LBM_ERR_ARG, "lbm_pbc_apply: needs nx >= 4 and non-null arrays");
+    if (int rc = set_device(device)) return rc;
+    const long long n = (long long)nx * ny;
+    DevBuf dr, du, df;
+    CK(dr.alloc(n * 8));
+    CK(du.alloc(n * 16));
+    CK(df.alloc(n * 72));
+    CK(cudaMemcpy(dr.p, rho, n * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(du.p, u, n * 16, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(df.p, f_pre, n * 72, cudaMemcpyHostToDevice));
+    k_pbc_apply_aos<<<(ny + 255) / 256, 256>>>(nx, ny, rho_in, rho_out, dr.as<double>(), du.as<double>(), df.as<double>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(f_pre, df.p, n * 72, cudaMemcpyDeviceToHost));
+    return LBM_OK;
+}
+
+// ---- context -------------------------------------------------------------------------------------------
+extern "C" int lbm_destroy(lbm_ctx *c)
+{
+    if (!c) return LBM_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->stream_edge) cudaStreamSynchronize(c->stream_edge);
+    for (int s = 0; s < 9; s++)
+        if (c->peer[s].mapped) {
+            bool shared = false;   // one mapping may serve several slots
+            for (int q = 0; q < s; q++) shared |= c->peer[q].mapped == c->peer[s].mapped;
+            if (!shared) cudaIpcCloseMemHandle(c->peer[s].mapped);
+        }
+    void *bufs[] = {c->arena,  c->kind_map, c->kinds,    c->ktab,   c->ctab,  c->outbuf[0],   c->outbuf[1], c->cells,
+                    c->done_counter, c->err_flag, c->stage_f, c->stage_rho, c->stage_u, c->mm_acc, c->probe};
+    for (void *b : bufs)
+        if (b) cudaFree(b);
+    if (c->ev_main) cudaEventDestroy(c->ev_main);
+    if (c->ev_edge) cudaEventDestroy(c->ev_edge);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->stream_edge) cudaStreamDestroy(c->stream_edge);
+    delete c;
+    return LBM_OK;
+}
+
+static int ctx_build(lbm_ctx *c, const lbm_bc_desc *bc)
+{
+    CK(cudaSetDevice(c->device));
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, lo));
+    CK(cudaStreamCreateWithPriority(&c->stream_edge, cudaStreamNonBlocking, hi));
+    CK(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_edge, cudaEventDisableTiming));
+
+    const size_t sbytes = (size_t)9 * c->plane * 8;
+    c->off_S[0] = 0;
+    c->off_S[1] = align_up(sbytes, 256);
+    c->off_flags = c->off_S[1] + align_up(sbytes, 256);
+    c->arena_bytes = c->off_flags + 256;
+    if (cudaMalloc(&c->arena, c->arena_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(LBM_ERR_NOMEM, "cannot allocate %.2f GB for a %dx%d lattice (two fp64 SoA buffers)", c->arena_bytes / 1e9,
+                    c->NX, c->NY);
+    }
+    c->S[0] = (double *)(c->arena + c->off_S[0]);
+    c->S[1] = (double *)(c->arena + c->off_S[1]);
+    c->flags_in = (unsigned *)(c->arena + c->off_flags);
+    CK(cudaMemset(c->arena + c->off_flags, 0, 256));
+    // padding columns are never read, but keep the buffers defined
+    CK(cudaMemsetAsync(c->S[0], 0, sbytes, c->stream));
+    CK(cudaMemsetAsync(c->S[1], 0, sbytes, c->stream));
+    CK(cudaMalloc(&c->done_counter, 8));
+    CK(cudaMalloc(&c->err_flag, 4));
+    CK(cudaMemset(c->done_counter, 0, 8));
+    CK(cudaMemset(c->err_flag, 0, 4));
+    CK(cudaMalloc(&c->mm_acc, 32));
+    for (int b = 0; b < 2; b++) {
+        CK(cudaMalloc(&c->outbuf[b], (size_t)3 * c->pitch * 8));
+        CK(cudaMemset(c->outbuf[b], 0, (size_t)3 * c->pitch * 8));
+    }
+
+    // staging: a chunk of rows in reference layout (96 B per cell), at most ~256 MB
+    long long rows = std::max<long long>(1, std::min<long long>(c->NX, (256LL << 20) / (96LL * c->NY)));
+    c->stage_cells = rows * c->NY;
+    CK(cudaMalloc(&c->stage_f, c->stage_cells * 72));
+    CK(cudaMalloc(&c->stage_rho, c->stage_cells * 8));
+    CK(cudaMalloc(&c->stage_u, c->stage_cells * 16));
+
+    if (bc && bc->kind_map) {
+        if (int rc = check_bc(bc)) return rc;
+        c->has_bc = true;
+        c->rho_in = bc->pbc_rho_in;
+        c->rho_out = bc->pbc_rho_out;
+        std::vector<uint8_t> km((size_t)c->NX * c->pitch, 0);
+        std::vector<int2> cells;
+        bool any_pbc = false;
+        for (int x = 0; x < c->NX; x++)
+            for (int y = 0; y < c->NY; y++) {
+                const uint8_t k = bc->kind_map[(size_t)x * c->NY + y];
+                if (k >= bc->n_kinds) return fail(LBM_ERR_ARG, "bc: kind_map[%d,%d] = %d out of range", x, y, k);
+                km[(size_t)x * c->pitch + y] = k;
+                if (k) {
+                    cells.push_back(make_int2(x, y));
+                    const lbm_kind &kd = bc->kinds[k];
+                    if (kd.flags & (LBM_CELL_PBC_IN_SRC | LBM_CELL_PBC_OUT_SRC)) {
+                        any_pbc = true;
+                        if ((kd.flags & LBM_CELL_PBC_IN_SRC) && x != c->NX - 2) return fail(LBM_ERR_ARG, "bc: PBC_IN_SRC cells must lie on row nx-2");
+                        if ((kd.flags & LBM_CELL_PBC_OUT_SRC) && x != 1) return fail(LBM_ERR_ARG, "bc: PBC_OUT_SRC cells must lie on row 1");
+                    }
+                    if ((c->gx && (x == 0 || x == c->NX - 1)) || (c->gy && (y == 0 || y == c->NY - 1)))
+                        return fail(LBM_ERR_ARG, "bc: ghost cells must be fluid (the reference applies its closures to the interior view)");
+                }
+            }
+        if (any_pbc && (c->gx || c->NX < 4)) return fail(LBM_ERR_ARG, "bc: pressure-periodic boundary needs nx >= 4 and no ghost rows");
+        CK(cudaMalloc(&c->kind_map, km.size()));
+        CK(cudaMemcpy(c->kind_map, km.data(), km.size(), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&c->kinds, bc->n_kinds * sizeof(lbm_kind)));
+        CK(cudaMemcpy(c->kinds, bc->kinds, bc->n_kinds * sizeof(lbm_kind), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&c->ktab, bc->n_k_rows * 72));
+        CK(cudaMemcpy(c->ktab, bc->k_table, bc->n_k_rows * 72, cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&c->ctab, std::max(bc->n_c_rows, 1) * 72));
+        if (bc->n_c_rows) CK(cudaMemcpy(c->ctab, bc->c_table, bc->n_c_rows * 72, cudaMemcpyHostToDevice));
+        c->n_cells = (int)cells.size();
+        if (c->n_cells) {
+            CK(cudaMalloc(&c->cells, cells.size() * sizeof(int2)));
+            CK(cudaMemcpy(c->cells, cells.data(), cells.size() * sizeof(int2), cudaMemcpyHostToDevice));
+        } else {
+            c->has_bc = false;
+        }
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return LBM_OK;
+}
+
+extern "C" int lbm_create(int device, int nx, int ny, int ghost_x, int ghost_y, const lbm_bc_desc *bc, lbm_ctx **out)
+{
+    if (!out) return fail(LBM_ERR_ARG, "lbm_create: out is null");
+    *out = nullptr;
+    if (nx < 1 || ny < 1) return fail(LBM_ERR_ARG, "lbm_create: lattice must be at least 1x1 (got %dx%d)", nx, ny);
+    if ((ghost_x | ghost_y) & ~1) return fail(LBM_ERR_ARG, "lbm_create: ghost width must be 0 or 1");
+    if ((ghost_x && nx < 3) || (ghost_y && ny < 3)) return fail(LBM_ERR_ARG, "lbm_create: a ghost ring needs at least one interior cell");
+    lbm_ctx *c = new lbm_ctx;
+    c->device = device;
+    c->NX = nx;
+    c->NY = ny;
+    c->gx = ghost_x;
+    c->gy = ghost_y;
+    c->pitch = (ny + 15) & ~15;
+    c->plane = (long long)nx * c->pitch;
+    if (int rc = ctx_build(c, bc)) {
+        std::string keep = g_err;
+        lbm_destroy(c);
+        g_err = keep;
+        return rc;
+    }
+    *out = c;
+    return LBM_OK;
+}
+
+extern "C" int lbm_set_bc_mode(lbm_ctx *c, int mode)
+{
+    if (!c || mode < LBM_BC_AUTO || mode > LBM_BC_EDGE) return fail(LBM_ERR_ARG, "lbm_set_bc_mode: bad argument");
+    c->bc_mode = mode;
+    return LBM_OK;
+}
+
+extern "C" int64_t lbm_device_bytes(const lbm_ctx *c) { return c ? (int64_t)c->arena_bytes + c->stage_cells * 96 : 0; }
+extern "C" void *lbm_stream(lbm_ctx *c) { return c ? (void *)c->stream : nullptr; }
+extern "C" int64_t lbm_time(const lbm_ctx *c) { return c ? c->t : -1; }
+extern "C" int64_t lbm_launch_count(const lbm_ctx *c) { return c ? c->launches : 0; }
+
+static bool use_mask(const lbm_ctx *c)
+{
+    if (!c->has_bc) return false;
+    if (c->bc_mode == LBM_BC_MASK) return true;
+    if (c->bc_mode == LBM_BC_EDGE) return false;
+    return (long long)c->NX * c->NY < kEdgeThreshold;
+}
+
+static void fill_common(const lbm_ctx *c, StepParams &P, int src_buf, int dst_buf, double omega)
+{
+    memset(&P, 0, sizeof P);
+    P.src = c->S[src_buf];
+    P.dst = c->S[dst_buf];
+    P.plane = c->plane;
+    P.pitch = c->pitch;
+    P.NX = c->NX;
+    P.NY = c->NY;
+    P.gx = c->gx;
+    P.gy = c->gy;
+    P.omega = omega;
+    P.kind_map = c->has_bc ? c->kind_map : nullptr;
+    P.kinds = c->kinds;
+    P.ktab = c->ktab;
+    P.ctab = c->ctab;
+    // outlet side buffers alternate with the S buffers: the kernel that reads S[b] reads outbuf[b]
+    P.out_cur = c->outbuf[src_buf];
+    P.out_next = c->outbuf[dst_buf];
+    P.rho_in = c->rho_in;
+    P.rho_out = c->rho_out;
+    P.px = -1;
+    P.py = -1;
+    P.cells = c->cells;
+    P.n_cells = c->n_cells;
+    P.done_counter = c->done_counter;
+    P.err_flag = c->err_flag;
+    P.flag_in = c->flags_in;
+}
+
+// arena offsets of a peer (its S[1] offset depends on ITS plane size)
+static size_t peer_off_S(const Peer &pr, int buf)
+{
+    const size_t sbytes = (size_t)9 * pr.nx * pr.pitch * 8;
+    return buf == 0 ? 0 : align_up(sbytes, 256);
+}
+static size_t peer_off_flags(const Peer &pr)
+{
+    const size_t sbytes = (size_t)9 * pr.nx * pr.pitch * 8;
+    return 2 * align_up(sbytes, 256);
+}
+
+static void fill_halo(const lbm_ctx *c, StepParams &P, int dst_buf, bool flags)
+{
+    for (int s = 0; s < 9; s++) {
+        P.halo[s].base = nullptr;
+        P.flag_out[s] = nullptr;
+        const Peer &pr = c->peer[s];
+        if (!c->halo_ready || !pr.connected) continue;
+        P.halo[s].base = (double *)(pr.arena + peer_off_S(pr, dst_buf));
+        P.halo[s].nx = pr.nx;
+        P.halo[s].ny = pr.ny;
+        P.halo[s].pitch = pr.pitch;
+        P.halo[s].plane = (long long)pr.nx * pr.pitch;
+        if (flags && pr.remote) {
+            // I am the neighbour's slot (8 - s): dx,dy mirrored
+            P.flag_out[s] = (unsigned *)(pr.arena + peer_off_flags(pr)) + (8 - s);
+        }
+    }
+}
+
+static int block_size(int w) { return w >= 256 ? 256 : std::max(32, (w + 31) & ~31); }
+
+template <bool MASK, bool HALO, bool FINAL, bool LIST>
+static cudaError_t launch(const StepParams &P, int blocks, int threads, cudaStream_t st)
+{
+    k_step<MASK, HALO, FINAL, LIST><<<blocks, threads, 0, st>>>(P);
+    return cudaGetLastError();
+}
+
+static int rows_launch(lbm_ctx *c, StepParams P, int row0a, int na, int row0b, int nb, bool mask, bool halo, cudaStream_t st)
+{
+    if (na + nb <= 0) return LBM_OK;
+    P.row0a = row0a;
+    P.na = na;
+    P.row0b = row0b;
+    P.y0 = c->gy;
+    P.y1 = c->NY - c->gy;
+    const int bs = block_size(P.y1 - P.y0);
+    P.bpr = (P.y1 - P.y0 + bs - 1) / bs;
+    const int blocks = (na + nb) * P.bpr;
+    P.n_blocks = blocks;
+    cudaError_t e;
+    if (mask)
+        e = halo ? launch<true, true, false, false>(P, blocks, bs, st) : launch<true, false, false, false>(P, blocks, bs, st);
+    else
+        e = halo ? launch<false, true, false, false>(P, blocks, bs, st) : launch<false, false, false, false>(P, blocks, bs, st);
+    if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "step kernel launch failed: %s", cudaGetErrorString(e));
+    c->launches++;
+    return LBM_OK;
+}
+
+// One reference time step: S[src] -> S[src^1]. `t_new` is the time index of the state being produced.
+static int one_step(lbm_ctx *c, int src, double omega, long long t_new)
+{
+    const int dst = src ^ 1;
+    StepParams P;
+    fill_common(c, P, src, dst, omega);
+    const bool mask = use_mask(c);
+    const bool fix = c->has_bc && !mask;   // mask-free kernel + thin fix-up kernel over the non-fluid cells
+    const bool halo = c->halo_ready;
+    const bool remote = halo && c->any_remote;
+    fill_halo(c, P, dst, true);
+    if (c->probe && c->px >= 0) {
+        P.px = c->px;
+        P.py = c->py;
+        P.probe_slot = c->probe + 2 * (t_new % c->probe_cap);
+    }
+    const int xlo = c->gx, xhi = c->NX - c->gx;   // interior rows [xlo, xhi)
+    // Flag protocol (remote neighbours only): a kernel that reads my ghosts / writes a neighbour's ghosts first
+    // waits until every neighbour has published epoch E (= it finished producing its S_t, hence finished reading
+    // the buffer I am about to overwrite), and the LAST kernel of the step that stores ghosts publishes E+1.
+    const unsigned E = c->halo_epoch;
+    const bool split = halo && c->gx && !c->gy && !fix && (xhi - xlo) >= 4 && (long long)c->NX * c->NY >= kEdgeThreshold;
+    if (!split) {
+        if (remote) {
+            P.wait_value = E;
+            P.signal_value = fix ? 0 : E + 1;
+        }
+        if (int rc = rows_launch(c, P, xlo, xhi - xlo, 0, 0, mask, halo, c->stream)) return rc;
+    } else {
+        // 1-D slabs: the two edge rows (the only readers of ghost rows and the only writers of neighbour ghosts)
+        // run on the high-priority stream; the interior overlaps with the NVLink stores they generate.
+        CK(cudaEventRecord(c->ev_main, c->stream));
+        CK(cudaStreamWaitEvent(c->stream_edge, c->ev_main, 0));   // everything queued so far (previous step's join)
+        StepParams Pe = P;
+        if (remote) {
+            Pe.wait_value = E;
+            Pe.signal_value = E + 1;
+        }
+        if (int rc = rows_launch(c, Pe, xlo, 1, xhi - 1, 1, mask, true, c->stream_edge)) return rc;
+        CK(cudaEventRecord(c->ev_edge, c->stream_edge));
+        StepParams Pi = P;
+        for (int s = 0; s < 9; s++) Pi.halo[s].base = nullptr;
+        if (int rc = rows_launch(c, Pi, xlo + 1, xhi - xlo - 2, 0, 0, mask, false, c->stream)) return rc;
+        CK(cudaStreamWaitEvent(c->stream, c->ev_edge, 0));        // join: the next step needs both
+    }
+    if (fix) {
+        StepParams L = P;
+        L.wait_value = 0;
+        L.signal_value = remote ? E + 1 : 0;
+        const int blocks = (c->n_cells + 127) / 128;
+        L.n_blocks = blocks;
+        cudaError_t e = halo ? launch<true, true, false, true>(L, blocks, 128, c->stream) : launch<true, false, false, true>(L, blocks, 128, c->stream);
+        if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "edge kernel launch failed: %s", cudaGetErrorString(e));
+        c->launches++;
+    }
+    if (remote) c->halo_epoch++;
+    return LBM_OK;
+}
+
+static int first_collide(lbm_ctx *c, InitParams &Q, int x0, int nrows)
+{
+    Q.x0 = x0;
+    Q.nrows = nrows;
+    const int bs = block_size(c->NY);
+    Q.S.bpr = (c->NY + bs - 1) / bs;
+    const int blocks = nrows * Q.S.bpr;
+    if (c->halo_ready)
+        k_first_collide<true><<<blocks, bs, 0, c->stream>>>(Q);
+    else
+        k_first_collide<false><<<blocks, bs, 0, c->stream>>>(Q);
+    CK(cudaGetLastError());
+    c->launches++;
+    return LBM_OK;
+}
+
+static int begin_load(lbm_ctx *c, double omega, InitParams &Q)
+{
+    if (!(omega > 0.0 && omega < 2.0)) return fail(LBM_ERR_ARG, "omega must satisfy 0 < omega < 2 (got %.17g)", omega);
+    if ((c->gx || c->gy) && !c->halo_ready)
+        return fail(LBM_ERR_STATE, "a lattice with a ghost ring needs its halo neighbours connected (lbm_halo_connect/finalize) before loading");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaStreamSynchronize(c->stream_edge));
+    memset(&Q, 0, sizeof Q);
+    c->cur = 0;
+    fill_common(c, Q.S, 1, 0, omega);   // "dst" = S[0]; outlet buffer written = outbuf[0], read by the first step
+    fill_halo(c, Q.S, 0, false);
+    return LBM_OK;
+}
+
+static int end_load(lbm_ctx *c, double omega)
+{
+    CK(cudaStreamSynchronize(c->stream));
+    c->loaded = true;
+    c->t = 0;
+    c->omega = omega;
+    // Ghost stores of the first collision are ordered against the first step by a host-side barrier the caller
+    // performs (python: process-group barrier after upload); flags restart from a common epoch.
+    return LBM_OK;
+}
+
+extern "C" int lbm_upload(lbm_ctx *c, const double *f, const double *rho, const double *u, double omega)
+{
+    if (!c || !f || !rho || !u) return fail(LBM_ERR_ARG, "lbm_upload: null pointer");
+    InitParams Q;
+    if (int rc = begin_load(c, omega, Q)) return rc;
+    const long long chunk_rows = c->stage_cells / c->NY;
+    for (int x0 = 0; x0 < c->NX; x0 += (int)chunk_rows) {
+        const int nr = (int)std::min<long long>(chunk_rows, c->NX - x0);
+        const size_t n = (size_t)nr * c->NY, o = (size_t)x0 * c->NY;
+        CK(cudaMemcpyAsync(c->stage_f, f + o * 9, n * 72, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->stage_rho, rho + o, n * 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->stage_u, u + o * 2, n * 16, cudaMemcpyHostToDevice, c->stream));
+        Q.in_f = c->stage_f;
+        Q.in_rho = c->stage_rho;
+        Q.in_u = c->stage_u;
+        if (int rc = first_collide(c, Q, x0, nr)) return rc;
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return end_load(c, omega);
+}
+
+extern "C" int lbm_init_equilibrium(lbm_ctx *c, const double *rho_x, const double *ux_y, double rho0, double ux0, double uy0,
+                                    double omega)
+{
+    if (!c) return fail(LBM_ERR_ARG, "lbm_init_equilibrium: null context");
+    InitParams Q;
+    if (int rc = begin_load(c, omega, Q)) return rc;
+    DevBuf dr, du;
+    if (rho_x) {
+        CK(dr.alloc((size_t)c->NX * 8));
+        CK(cudaMemcpy(dr.p, rho_x, (size_t)c->NX * 8, cudaMemcpyHostToDevice));
+        Q.rho_x = dr.as<double>();
+    }
+    if (ux_y) {
+        CK(du.alloc((size_t)c->NY * 8));
+        CK(cudaMemcpy(du.p, ux_y, (size_t)c->NY * 8, cudaMemcpyHostToDevice));
+        Q.ux_y = du.as<double>();
+    }
+    Q.rho0 = rho0;
+    Q.ux0 = ux0;
+    Q.uy0 = uy0;
+    if (int rc = first_collide(c, Q, 0, c->NX)) return rc;
+    return end_load(c, omega);
+}
+
+extern "C" int lbm_step(lbm_ctx *c, double omega, int n_steps)
+{
+    if (!c) return fail(LBM_ERR_ARG, "lbm_step: null context");
+    if (!(omega > 0.0 && omega < 2.0)) return fail(LBM_ERR_ARG, "omega must satisfy 0 < omega < 2 (got %.17g)", omega);
+    if (n_steps < 0) return fail(LBM_ERR_ARG, "lbm_step: n_steps < 0");
+    if (!c->loaded) return fail(LBM_ERR_STATE, "lbm_step before lbm_upload / lbm_init_equilibrium");
+    if (n_steps == 0) return LBM_OK;
+    CK(cudaSetDevice(c->device));
+    if (omega != c->omega) {
+        // S[cur] was collided with the previous call's omega. Redo that collision from the retained S_{t-1}.
+        if (c->t == 0) return fail(LBM_ERR_STATE, "omega differs from the one given at upload and no step has been taken: upload again");
+        if (c->any_remote) return fail(LBM_ERR_STATE, "changing omega between steps is not supported with remote halo neighbours: upload again");
+        if (int rc = one_step(c, c->cur ^ 1, omega, c->t)) return rc;
+        c->omega = omega;
+    }
+    for (int i = 0; i < n_steps; i++) {
+        if (int rc = one_step(c, c->cur, omega, c->t + 1)) return rc;
+        c->cur ^= 1;
+        c->t++;
+    }
+    return LBM_OK;
+}
+
+extern "C" int lbm_sync(lbm_ctx *c)
+{
+    if (!c) return fail(LBM_ERR_ARG, "lbm_sync: null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream_edge));
+    CK(cudaStreamSynchronize(c->stream));
+    unsigned err = 0;
+    CK(cudaMemcpy(&err, c->err_flag, 4, cudaMemcpyDeviceToHost));
+    if (err) {
+        cudaMemset(c->err_flag, 0, 4);
+        return fail(LBM_ERR_TIMEOUT, "halo flag wait timed out: a neighbouring rank did not take the same step");
+    }
+    return LBM_OK;
+}
+
+// f_post / rho / u of time t are stream+BC+moments of S_{t-1}, which the A/B scheme still holds in S[cur^1].
+static int materialize_rows(lbm_ctx *c, int x0, int x1, int y0, int y1, double *f, double *rho, double *u, bool to_host)
+{
+    StepParams P;
+    fill_common(c, P, c->cur ^ 1, c->cur, c->omega);
+    const int w = y1 - y0;
+    const long long chunk_rows = std::max<long long>(1, c->stage_cells / w);
+    for (int xa = x0; xa < x1; xa += (int)chunk_rows) {
+        const int nr = (int)std::min<long long>(chunk_rows, x1 - xa);
+        P.row0a = xa;
+        P.na = nr;
+        P.y0 = y0;
+        P.y1 = y1;
+        const int bs = block_size(w);
+        P.bpr = (w + bs - 1) / bs;
+        P.ox0 = xa;
+        P.oy0 = y0;
+        P.ow = w;
+        P.o_f = f ? c->stage_f : nullptr;
+        P.o_rho = rho || !to_host ? c->stage_rho : nullptr;
+        P.o_u = u || !to_host ? c->stage_u : nullptr;
+        const int blocks = nr * P.bpr;
+        cudaError_t e = c->has_bc ? launch<true, false, true, false>(P, blocks, bs, c->stream) : launch<false, false, true, false>(P, blocks, bs, c->stream);
+        if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "materialize kernel launch failed: %s", cudaGetErrorString(e));
+        c->launches++;
+        const size_t n = (size_t)nr * w, o = (size_t)(xa - x0) * w;
+        if (to_host) {
+            if (f) CK(cudaMemcpyAsync(f + o * 9, c->stage_f, n * 72, cudaMemcpyDeviceToHost, c->stream));
+            if (rho) CK(cudaMemcpyAsync(rho + o, c->stage_rho, n * 8, cudaMemcpyDeviceToHost, c->stream));
+            if (u) CK(cudaMemcpyAsync(u + o * 2, c->stage_u, n * 16, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+        } else {
+            const int nb = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+            k_minmax<<<nb, 256, 0, c->stream>>>((long long)n, c->stage_rho, c->stage_u, c->mm_acc);
+            CK(cudaGetLastError());
+            c->launches++;
+            CK(cudaStreamSynchronize(c->stream));
+        }
+    }
+    return LBM_OK;
+}
+
+static int check_region(lbm_ctx *c, int x0, int x1, int y0, int y1, const char *who)
+{
+    if (!c) return fail(LBM_ERR_ARG, "%s: null context", who);
+    if (!c->loaded || c->t == 0) return fail(LBM_ERR_STATE, "%s: no step taken since the state was loaded — the caller still holds it", who);
+    if (x0 < 0 || y0 < 0 || x1 > c->NX || y1 > c->NY || x0 >= x1 || y0 >= y1) return fail(LBM_ERR_ARG, "%s: empty or out-of-range region", who);
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream_edge));
+    return LBM_OK;
+}
+
+extern "C" int lbm_materialize_region(lbm_ctx *c, int x0, int x1, int y0, int y1, double *f, double *rho, double *u)
+{
+    if (int rc = check_region(c, x0, x1, y0, y1, "lbm_materialize")) return rc;
+    if (!f && !rho && !u) return LBM_OK;
+    return materialize_rows(c, x0, x1, y0, y1, f, rho, u, true);
+}
+
+extern "C" int lbm_materialize(lbm_ctx *c, double *f, double *rho, double *u)
+{
+    if (!c) return fail(LBM_ERR_ARG, "lbm_materialize: null context");
+    return lbm_materialize_region(c, 0, c->NX, 0, c->NY, f, rho, u);
+}
+
+extern "C" int lbm_minmax(lbm_ctx *c, int x0, int x1, int y0, int y1, double out[4])
+{
+    if (int rc = check_region(c, x0, x1, y0, y1, "lbm_minmax")) return rc;
+    if (!out) return fail(LBM_ERR_ARG, "lbm_minmax: out is null");
+    const long long init[4] = {0x7fffffffffffffffLL, -0x7fffffffffffffffLL - 1, 0x7fffffffffffffffLL, -0x7fffffffffffffffLL - 1};
+    CK(cudaMemcpyAsync(c->mm_acc, init, 32, cudaMemcpyHostToDevice, c->stream));
+    if (int rc = materialize_rows(c, x0, x1, y0, y1, nullptr, nullptr, nullptr, false)) return rc;
+    long long acc[4];
+    CK(cudaMemcpy(acc, c->mm_acc, 32, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 4; i++) out[i] = unord(acc[i]);
+    return LBM_OK;
+}
+
+extern "C" int lbm_probe_config(lbm_ctx *c, int x, int y, int capacity)
+{
+    if (!c) return fail(LBM_ERR_ARG, "lbm_probe_config: null context");
+    if (x < 0 || y < 0 || x >= c->NX || y >= c->NY || capacity < 1) return fail(LBM_ERR_ARG, "lbm_probe_config: probe outside the lattice or capacity < 1");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->probe) CK(cudaFree(c->probe));
+    c->probe = nullptr;
+    CK(cudaMalloc(&c->probe, (size_t)capacity * 16));
+    CK(cudaMemset(c->probe, 0, (size_t)capacity * 16));
+    c->px = x;
+    c->py = y;
+    c->probe_cap = capacity;
+    return LBM_OK;
+}
+
+extern "C" int lbm_probe_read(lbm_ctx *c, int64_t t0, int n, double *uxuy)
+{
+    if (!c || !uxuy) return fail(LBM_ERR_ARG, "lbm_probe_read: null pointer");
+    if (!c->probe) return fail(LBM_ERR_STATE, "lbm_probe_read: no probe configured");
+    if (n < 0 || t0 < 1 || t0 + n - 1 > c->t || c->t - t0 >= c->probe_cap)
+        return fail(LBM_ERR_ARG, "lbm_probe_read: steps [%lld, %lld) not in the ring (time %lld, capacity %d)", (long long)t0,
+                    (long long)t0 + n, c->t, c->probe_cap);
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream_edge));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n;) {
+        const int slot = (int)((t0 + i) % c->probe_cap);
+        const int run = std::min(n - i, c->probe_cap - slot);
+        CK(cudaMemcpy(uxuy + 2 * i, c->probe + 2 * slot, (size_t)run * 16, cudaMemcpyDeviceToHost));
+        i += run;
+    }
+    return LBM_OK;
+}
+
+// ---- halo ----------------------------------------------------------------------------------------------
+extern "C" int lbm_halo_export_handle(lbm_ctx *c, lbm_halo_export *out)
+{
+    if (!c || !out) return fail(LBM_ERR_ARG, "lbm_halo_export_handle: null pointer");
+    memset(out, 0, sizeof *out);
+    CK(cudaSetDevice(c->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) <= LBM_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, c->arena) == cudaSuccess)
+        memcpy(out->mem_handle, &h, sizeof h);
+    else
+        cudaGetLastError();   // IPC unavailable (e.g. some containers): same-process neighbours still work
+    out->device = c->device;
+    out->nx = c->NX;
+    out->ny = c->NY;
+    out->pitch = c->pitch;
+    out->pid = (int64_t)getpid();
+    out->arena_ptr = (uint64_t)(uintptr_t)c->arena;
+    out->arena_bytes = (int64_t)c->arena_bytes;
+    return LBM_OK;
+}
+
+extern "C" int lbm_halo_connect(lbm_ctx *c, int slot, const lbm_halo_export *peer)
+{
+    if (!c || !peer) return fail(LBM_ERR_ARG, "lbm_halo_connect: null pointer");
+    if (slot < 0 || slot > 8 || slot == 4) return fail(LBM_ERR_ARG, "lbm_halo_connect: slot must be 0..8 except 4");
+    const int dx = slot / 3 - 1, dy = slot % 3 - 1;
+    if ((dx && !c->gx) || (dy && !c->gy)) return fail(LBM_ERR_ARG, "lbm_halo_connect: no ghost layer in that direction");
+    // an x-neighbour shares my y extent and vice versa (Cartesian blocks, parallelization_utils.py:111-120)
+    if (dx == 0 && peer->nx != c->NX) return fail(LBM_ERR_ARG, "lbm_halo_connect: y-neighbour must have the same nx");
+    if (dy == 0 && peer->ny != c->NY) return fail(LBM_ERR_ARG, "lbm_halo_connect: x-neighbour must have the same ny");
+    CK(cudaSetDevice(c->device));
+    Peer &pr = c->peer[slot];
+    pr.nx = peer->nx;
+    pr.ny = peer->ny;
+    pr.pitch = peer->pitch;
+    if (peer->pid == (int64_t)getpid()) {
+        pr.arena = (char *)(uintptr_t)peer->arena_ptr;
+        pr.remote = pr.arena != c->arena;
+        if (pr.remote && peer->device != c->device) {
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, c->device, peer->device));
+            if (!can) return fail(LBM_ERR_CUDA, "device %d cannot access device %d", c->device, peer->device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+            cudaGetLastError();
+        }
+    } else {
+        // reuse a mapping of the same peer opened for another slot (cudaIpcOpenMemHandle is once per process)
+        void *m = nullptr;
+        static thread_local std::vector<std::pair<std::string, void *>> opened;
+        const std::string key((const char *)peer->mem_handle, LBM_IPC_HANDLE_BYTES);
+        for (auto &kv : opened)
+            if (kv.first == key) m = kv.second;
+        if (!m) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, peer->mem_handle, sizeof h);
+            CK(cudaIpcOpenMemHandle(&m, h, cudaIpcMemLazyEnablePeerAccess));
+            opened.emplace_back(key, m);
+        }
+        pr.mapped = m;
+        pr.arena = (char *)m;
+        pr.remote = true;
+    }
+    pr.connected = true;
+    return LBM_OK;
+}
+
+extern "C" int lbm_halo_finalize(lbm_ctx *c)
+{
+    if (!c) return fail(LBM_ERR_ARG, "lbm_halo_finalize: null context");
+    for (int dx = -1; dx <= 1; dx++)
+        for (int dy = -1; dy <= 1; dy++) {
+            if (!dx && !dy) continue;
+            const bool needed = (!dx || c->gx) && (!dy || c->gy);
+            if (needed && !c->peer[(dx + 1) * 3 + dy + 1].connected)
+                return fail(LBM_ERR_STATE, "lbm_halo_finalize: neighbour (%d,%d) not connected", dx, dy);
+        }
+    c->any_remote = false;
+    for (int s = 0; s < 9; s++) c->any_remote |= c->peer[s].connected && c->peer[s].remote;
+    c->halo_ready = true;
+    c->halo_epoch = 0;
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemset(c->arena + c->off_flags, 0, 256));
+    return LBM_OK;
+}

@@ -1,0 +1,319 @@
+"""Device-resident lattice + the lazy result handles `lattice_boltzmann_step` returns.
+
+`Lattice` is a thin object over one `lbm_ctx` of the C-ABI (include/lbm_b200.h). `LatticeArray` is what the
+drop-in `lattice_boltzmann_step` hands back in place of the reference's three fresh numpy arrays
+(src/lattice_boltzmann_method.py:225-228): an ndarray-like handle on "f / density / velocity at time t of this
+lattice" which is only copied to the host when somebody looks at it. Feeding the three handles straight back
+into the next call — what every driver loop of the reference does — costs one kernel launch and
+no transfer.
+
+Safety rule: the device keeps S_{t-1} and S_t (A/B buffers); values of time t are reconstructed from S_{t-1}.
+Before the device advances past t, every handle of time t that is still referenced anywhere is materialised
+(weak references tell). To make that cheap in the common loop `f, rho, u = step(f, rho, u, ...)`, the launch of
+a step is deferred until the next call or the first access: by then the loop has dropped the old handles.
+"""
+import weakref
+
+import numpy as np
+
+from . import _native as N
+
+
+class Lattice:
+    """One device-resident lattice (one `lbm_ctx`). Native API for callers that do not need the reference's
+    per-step Python protocol: `load`, `run(n)`, `fields()`, `probe`, `minmax`."""
+
+    def __init__(self, nx, ny, kind_map=None, ghost=(0, 0), device=None, bc_mode=N.BC_AUTO):
+        self.lib = N.load()
+        self.device = N.device() if device is None else int(device)
+        self.nx, self.ny = int(nx), int(ny)
+        self.ghost = (int(ghost[0]), int(ghost[1]))
+        self._ctx = N._CTX()
+        desc_ref = None
+        if kind_map is not None and not kind_map.is_trivial:
+            assert kind_map.shape == (self.nx, self.ny)
+            desc, self._keep = kind_map.to_desc()
+            desc_ref = N.C.byref(desc)
+        N.check(self.lib.lbm_create(self.device, self.nx, self.ny, self.ghost[0], self.ghost[1], desc_ref,
+                                    N.C.byref(self._ctx)))
+        self._keep = None
+        if bc_mode != N.BC_AUTO:
+            N.check(self.lib.lbm_set_bc_mode(self._ctx, bc_mode))
+        self.omega = None
+        self.time = 0                 # reference steps taken on the device since load
+        self._probe = None
+        self._probe_t0 = 0
+        # lazy-handle bookkeeping (see module docstring)
+        self._pending = None          # omega of a step requested but not yet launched
+        self._handles = {}            # api time -> list of weakrefs to LatticeArray
+        self._base = {}               # api time 0 arrays (the caller's own numpy arrays)
+
+    # ---- lifetime ----------------------------------------------------------------------------------------
+    def close(self):
+        if self._ctx:
+            self.lib.lbm_destroy(self._ctx)
+            self._ctx = N._CTX()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- native API --------------------------------------------------------------------------------------
+    @property
+    def shape(self):
+        return (self.nx, self.ny)
+
+    @property
+    def stream(self):
+        """cudaStream_t (int) the step kernels run on — wrap with torch.cuda.ExternalStream for event timing."""
+        return int(self.lib.lbm_stream(self._ctx) or 0)
+
+    @property
+    def device_bytes(self):
+        return int(self.lib.lbm_device_bytes(self._ctx))
+
+    @property
+    def launches(self):
+        return int(self.lib.lbm_launch_count(self._ctx))
+
+    def load(self, f, rho, u, omega):
+        """State triple of the reference (f, density, velocity) -> device; first collision with the given moments."""
+        f = N.as_f64(f, (self.nx, self.ny, 9), 'f')
+        rho = N.as_f64(rho, (self.nx, self.ny), 'density')
+        u = N.as_f64(u, (self.nx, self.ny, 2), 'velocity')
+        assert 0 < omega < 2
+        N.check(self.lib.lbm_upload(self._ctx, N.dptr(f), N.dptr(rho), N.dptr(u), float(omega)))
+        self.omega, self.time = float(omega), 0
+
+    def load_equilibrium(self, omega, rho_x=None, ux_y=None, rho0=1.0, ux0=0.0, uy0=0.0):
+        """f = f_eq(rho, u) of a separable initial field, built on the device (initial_values.py:38-123)."""
+        rx = N.as_f64(rho_x, (self.nx,), 'rho_x') if rho_x is not None else None
+        uy = N.as_f64(ux_y, (self.ny,), 'ux_y') if ux_y is not None else None
+        assert 0 < omega < 2
+        N.check(self.lib.lbm_init_equilibrium(self._ctx, N.dptr(rx), N.dptr(uy), float(rho0), float(ux0), float(uy0),
+                                              float(omega)))
+        self.omega, self.time = float(omega), 0
+
+    def run(self, n_steps, omega=None):
+        """n reference time steps, asynchronous."""
+        omega = self.omega if omega is None else float(omega)
+        assert 0 < omega < 2
+        N.check(self.lib.lbm_step(self._ctx, omega, int(n_steps)))
+        self.omega = omega
+        self.time += int(n_steps)
+
+    def sync(self):
+        N.check(self.lib.lbm_sync(self._ctx))
+
+    def fields(self, f=True, rho=True, u=True, region=None):
+        """Reference-layout (f_post, density, velocity) of the current time; None for the ones not asked for."""
+        x0, x1, y0, y1 = (0, self.nx, 0, self.ny) if region is None else region
+        n = (x1 - x0, y1 - y0)
+        of = np.empty(n + (9,)) if f else None
+        orho = np.empty(n) if rho else None
+        ou = np.empty(n + (2,)) if u else None
+        N.check(self.lib.lbm_materialize_region(self._ctx, x0, x1, y0, y1, N.dptr(of), N.dptr(orho), N.dptr(ou)))
+        return of, orho, ou
+
+    def probe(self, x, y, capacity=1 << 16):
+        """Record (u_x, u_y) at one cell after every step (experiments.py:703-704)."""
+        N.check(self.lib.lbm_probe_config(self._ctx, int(x), int(y), int(capacity)))
+        self._probe = (int(x), int(y), int(capacity))
+
+    def probe_read(self, t0, n):
+        out = np.empty((n, 2))
+        N.check(self.lib.lbm_probe_read(self._ctx, int(t0), int(n), N.dptr(out)))
+        return out
+
+    def minmax(self, region=None):
+        """(min rho, max rho, min u, max u) of the current state, reduced on the device (experiments.py:181-193)."""
+        x0, x1, y0, y1 = (0, self.nx, 0, self.ny) if region is None else region
+        out = np.empty(4)
+        N.check(self.lib.lbm_minmax(self._ctx, x0, x1, y0, y1, N.dptr(out)))
+        return tuple(out)
+
+    def halo_export(self):
+        e = N.HaloExport()
+        N.check(self.lib.lbm_halo_export_handle(self._ctx, N.C.byref(e)))
+        return e
+
+    def halo_connect(self, slot, export):
+        N.check(self.lib.lbm_halo_connect(self._ctx, int(slot), N.C.byref(export)))
+
+    def halo_finalize(self):
+        N.check(self.lib.lbm_halo_finalize(self._ctx))
+
+    def connect_self_periodic(self):
+        """One rank: every neighbour is this lattice itself (communication() with a 1x1 topology)."""
+        e = self.halo_export()
+        for dx in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                if (dx or dy) and (not dx or self.ghost[0]) and (not dy or self.ghost[1]):
+                    self.halo_connect((dx + 1) * 3 + dy + 1, e)
+        self.halo_finalize()
+
+    # ---- lazy-handle protocol used by lattice_boltzmann_step ------------------------------------------------
+    @property
+    def api_time(self):
+        return self.time + (1 if self._pending is not None else 0)
+
+    def _live(self, t):
+        refs = self._handles.get(t, ())
+        return [h for h in (r() for r in refs) if h is not None]
+
+    def _preserve(self, t):
+        """Materialise every still-referenced handle of device time t (must be the current device time)."""
+        live = [h for h in self._live(t) if h._value is None]
+        if live and t == self.time and t > 0:
+            want = {h._which for h in live}
+            f, rho, u = self.fields('f' in want, 'rho' in want, 'u' in want)
+            for h in live:
+                h._value = {'f': f, 'rho': rho, 'u': u}[h._which]
+                h._value.setflags(write=False)
+        self._handles.pop(t, None)
+
+    def flush(self):
+        """Launch the deferred step, if any."""
+        if self._pending is not None:
+            omega, self._pending = self._pending, None
+            self._preserve(self.time)
+            self.run(1, omega)
+
+    def request_step(self, omega):
+        """Called by lattice_boltzmann_step: returns the three handles of the next time."""
+        self.flush()
+        self._pending = float(omega)
+        t = self.api_time
+        hs = tuple(LatticeArray(self, t, which) for which in ('f', 'rho', 'u'))
+        self._handles[t] = [weakref.ref(h) for h in hs]
+        return hs
+
+    def reset_for_upload(self):
+        """Before a fresh upload: nothing pending may be lost, nothing referenced may go stale."""
+        self.flush()
+        self._preserve(self.time)
+        self._handles.clear()
+
+    def is_current(self, *handles):
+        t = self.api_time
+        return all(isinstance(h, LatticeArray) and h._lattice is self and h._t == t and not h._dirty
+                   for h in handles)
+
+
+_SHAPES = {'f': lambda nx, ny: (nx, ny, 9), 'rho': lambda nx, ny: (nx, ny), 'u': lambda nx, ny: (nx, ny, 2)}
+
+
+class LatticeArray(np.lib.mixins.NDArrayOperatorsMixin):
+    """ndarray-like view of one field of a `Lattice` at one time. Read-only until materialised; any numpy
+    operation materialises it (one device->host copy, cached) — except scalar cell reads and whole-field
+    np.amin / np.amax, which are answered from the device."""
+
+    __array_priority__ = 100
+
+    def __init__(self, lattice, t, which):
+        self._lattice, self._t, self._which = lattice, t, which
+        self._value = None
+        self._dirty = False           # written through __setitem__: the device copy no longer matches
+        self.shape = _SHAPES[which](lattice.nx, lattice.ny)
+        self.dtype = np.dtype(np.float64)
+
+    ndim = property(lambda self: len(self.shape))
+    size = property(lambda self: int(np.prod(self.shape)))
+
+    def _bring_current(self):
+        L = self._lattice
+        if self._value is None:
+            if self._t == L.api_time and L._pending is not None:
+                L.flush()
+            if self._t != L.time:
+                raise RuntimeError('stale LatticeArray: the lattice advanced without this handle being preserved '
+                                   '(internal error)')
+
+    def materialize(self):
+        if self._value is None:
+            self._bring_current()
+            L = self._lattice
+            f, rho, u = L.fields(self._which == 'f', self._which == 'rho', self._which == 'u')
+            self._value = {'f': f, 'rho': rho, 'u': u}[self._which]
+            self._value.setflags(write=False)   # in-place edits must go through __setitem__ (tracked)
+        return self._value
+
+    # numpy protocols ----------------------------------------------------------------------------------------
+    def __array__(self, dtype=None, copy=None):
+        a = self.materialize()
+        if dtype is not None and np.dtype(dtype) != a.dtype:
+            return a.astype(dtype)
+        return a.copy() if copy else a
+
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        inputs = tuple(x.materialize() if isinstance(x, LatticeArray) else x for x in inputs)
+        if 'out' in kwargs:
+            kwargs['out'] = tuple(x.materialize() if isinstance(x, LatticeArray) else x for x in kwargs['out'])
+        return getattr(ufunc, method)(*inputs, **kwargs)
+
+    def __array_function__(self, func, types, args, kwargs):
+        if func in (np.amin, np.amax, np.min, np.max) and len(args) == 1 and not kwargs and args[0] is self \
+                and self._value is None and self._which in ('rho', 'u'):
+            return self._extremum(func in (np.amax, np.max))
+
+        def conv(x):
+            if isinstance(x, LatticeArray):
+                return x.materialize()
+            if isinstance(x, (list, tuple)):
+                return type(x)(conv(v) for v in x)
+            return x
+        return func(*conv(args), **{k: conv(v) for k, v in kwargs.items()})
+
+    def _extremum(self, want_max):
+        self._bring_current()
+        mn_r, mx_r, mn_u, mx_u = self._lattice.minmax()
+        if self._which == 'rho':
+            return np.float64(mx_r if want_max else mn_r)
+        return np.float64(mx_u if want_max else mn_u)
+
+    def min(self, *a, **k):
+        return self._extremum(False) if not a and not k and self._value is None and self._which != 'f' else \
+            self.materialize().min(*a, **k)
+
+    def max(self, *a, **k):
+        return self._extremum(True) if not a and not k and self._value is None and self._which != 'f' else \
+            self.materialize().max(*a, **k)
+
+    def __getitem__(self, index):
+        if self._value is None and isinstance(index, tuple) and len(index) >= 2:
+            ix, iy = index[0], index[1]
+            if isinstance(ix, (int, np.integer)) and isinstance(iy, (int, np.integer)):
+                # velocity[px, py, ...] every step (experiments.py:703-704): fetch one cell, not the lattice
+                self._bring_current()
+                L = self._lattice
+                x, y = int(ix) % L.nx, int(iy) % L.ny
+                f, rho, u = L.fields(self._which == 'f', self._which == 'rho', self._which == 'u', (x, x + 1, y, y + 1))
+                cell = {'f': f, 'rho': rho, 'u': u}[self._which][0, 0]
+                rest = tuple(i for i in index[2:] if i is not Ellipsis)
+                return cell[rest] if rest else (cell if self._which != 'rho' else np.float64(cell))
+        return self.materialize()[index]
+
+    def __setitem__(self, index, value):
+        a = self.materialize()
+        if not a.flags.writeable:
+            a = self._value = a.copy()
+        self._dirty = True
+        a[index] = value
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __iter__(self):
+        return iter(self.materialize())
+
+    def __getattr__(self, name):
+        # anything else an ndarray offers (copy, sum, mean, T, astype, tobytes, ...)
+        if name.startswith('_'):
+            raise AttributeError(name)
+        return getattr(self.materialize(), name)
+
+    def __repr__(self):
+        state = 'host' if self._value is not None else 'device'
+        return f'LatticeArray({self._which}, t={self._t}, shape={self.shape}, {state})'

@@ -1,0 +1,494 @@
+"""Parity of the CUDA path (through the C-ABI, via the reference-shaped Python API) against the pinned oracle and
+the reference-generated golden fixtures. Bit-exact everywhere (every operation is an IEEE add/mul/div/sqrt in the
+reference's order); the bar BASELINE.json states is 1e-12 relative after 1000 steps (tests/helpers.py:RTOL).
+Runs on the B200 box: `pytest -m gpu`."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.helpers import assert_parity, sha
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+
+
+@pytest.fixture(scope='module')
+def P():
+    import lattice_boltzmann_parallel_solver_b200 as pkg
+    from lattice_boltzmann_parallel_solver_b200 import _native
+    _native.device()   # raises loudly when there is no GPU / no library
+    yield pkg
+    pkg.lattice_boltzmann_method.release_lattices()
+
+
+@pytest.fixture(scope='module')
+def oracle():
+    from oracle import lbm_c, lbm_numpy
+
+    class O:
+        c = lbm_c
+        np = lbm_numpy
+    return O
+
+
+def check_digests(g, tag, f, rho, u):
+    assert sha(np.asarray(f)) == str(g[tag + '_f']), tag + ' f'
+    assert sha(np.asarray(rho)) == str(g[tag + '_rho']), tag + ' rho'
+    assert sha(np.asarray(u)) == str(g[tag + '_u']), tag + ' u'
+
+
+# ---------------------------------------------------------------------------------------------------------
+# a2-a5: stateless kernels
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('n', ['a', 'b'])
+def test_kernels_vs_reference_golden(P, n):
+    L = P.lattice_boltzmann_method
+    g = load('kernels.npz')
+    rho, u, f = g[n + '_rho'], g[n + '_u'], g[n + '_f']
+    assert_parity(L.equilibrium_distr_func(rho, u), g[n + '_feq'], 'feq')
+    assert_parity(L.compute_density(f), g[n + '_density'], 'density')
+    assert_parity(L.compute_velocity_field(rho, f), g[n + '_velocity'], 'velocity')
+    assert_parity(L.streaming(f), g[n + '_stream'], 'streaming')
+    f2, r2, u2 = L.lattice_boltzmann_step(f, rho, u, 1.3)
+    assert_parity(f2, g[n + '_step_f'], 'step f')
+    assert_parity(r2, g[n + '_step_rho'], 'step rho')
+    assert_parity(u2, g[n + '_step_u'], 'step u')
+
+
+def test_equilibrium_1d_inputs(P, oracle):
+    """boundary_conditions.py:338 calls it with (ly,), (ly,2) and gets (1, ly, 9)."""
+    L = P.lattice_boltzmann_method
+    rng = np.random.default_rng(5)
+    rho, u = rng.uniform(0.9, 1.1, 13), rng.uniform(-0.1, 0.1, (13, 2))
+    out = L.equilibrium_distr_func(rho, u)
+    assert out.shape == (1, 13, 9)
+    assert_parity(out[0], oracle.np.equilibrium(rho, u), '1-D feq')
+
+
+def test_step_asserts(P):
+    L = P.lattice_boltzmann_method
+    f, rho, u = np.ones((4, 4, 9)), np.ones((4, 4)), np.zeros((4, 4, 2))
+    for om in (0, 2, -1, 2.5):
+        with pytest.raises(AssertionError):
+            L.lattice_boltzmann_step(f, rho, u, om)
+    with pytest.raises(AssertionError):
+        L.lattice_boltzmann_step(f, np.ones((4, 5)), u, 1.0)
+    with pytest.raises(AssertionError):
+        L.compute_density(np.ones((4, 4, 8)))
+    with pytest.raises(TypeError):
+        L.lattice_boltzmann_step(f, rho, u, 1.0, boundary=lambda *a: a[1])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference unit tests re-pointed at the new module (tests/test_*.py of the reference)
+# ---------------------------------------------------------------------------------------------------------
+def test_reference_unit_invariants(P):
+    L = P.lattice_boltzmann_method
+    # test_density_computation.py:12-18 / test_velocity_computation.py:12-20
+    f = np.ones((10, 10, 9)) / 9
+    assert round(float(np.sum(L.compute_density(f))), 1) == 100.0
+    assert round(float(np.sum(L.compute_velocity_field(L.compute_density(f), f))), 1) == 0.0
+    # test_streaming_func.py:12-38
+    rng = np.random.default_rng(0)
+    for g in (np.ones((12, 9, 9)), rng.uniform(0, 1, (12, 9, 9))):
+        assert abs(float(np.sum(L.streaming(g)) - np.sum(g))) < 1e-9
+    one = np.zeros((12, 9, 9))
+    one[3, 4, 5] = 1.0
+    assert L.streaming(one)[4, 5, 5] == 1.0
+    # test_navier_stokes_eq.py:12-51
+    rho = rng.uniform(0.5, 1.5, (10, 10))
+    u = rng.uniform(-0.1, 0.1, (10, 10, 2))
+    feq = L.equilibrium_distr_func(rho, u)
+    assert np.allclose(feq.sum(-1), rho)
+    assert np.allclose(feq @ L.get_velocity_sets(), rho[..., None] * u)
+    assert L.get_velocity_sets().sum() == 0
+
+
+def test_mass_preservation_10000_steps(P):
+    """tests/test_mass_preservation.py:22-34: 50x50, omega 0.5, point perturbation, 10 000 periodic steps."""
+    L = P.lattice_boltzmann_method
+    rho = np.ones((50, 50)) * 0.5
+    rho[25, 25] = 0.6
+    u = np.zeros((50, 50, 2))
+    f = L.equilibrium_distr_func(rho, u)
+    m0 = float(np.sum(rho))
+    for _ in range(10000):
+        f, rho, u = L.lattice_boltzmann_step(f, rho, u, 0.5)
+    assert round(float(np.sum(np.asarray(rho))), 1) == round(m0, 1)
+    assert abs(float(np.sum(np.asarray(f))) - m0) < 1e-8
+
+
+# ---------------------------------------------------------------------------------------------------------
+# a6-a11: boundary closures called directly (tests/test_boundary_conditions.py of the reference)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('n', ['s', 'r'])
+def test_bc_primitives_vs_reference_golden(P, n):
+    B, BU = P.boundary_conditions, P.boundary_utils
+    g = load('bc_primitives.npz')
+    f_pre, f_post, f_prev, rho, u = (g[n + k] for k in ('_f_pre', '_f_post', '_f_prev', '_rho', '_u'))
+    nx, ny = rho.shape
+
+    def edge(w):
+        m = np.zeros((nx, ny), dtype=bool)
+        if w == 'x0':
+            m[0, :] = True
+        elif w == 'x1':
+            m[-1, :] = True
+        elif w == 'y0':
+            m[:, 0] = True
+        else:
+            m[:, -1] = True
+        return m
+
+    for w in ('x0', 'x1', 'y0', 'y1'):
+        assert_parity(B.rigid_wall(edge(w))(f_pre.copy(), f_post.copy()), g[f'{n}_rigid_{w}'], 'rigid ' + w)
+        assert_parity(B.moving_wall(edge(w), np.array([0.05, -0.02]), 1.03)(f_pre.copy(), f_post.copy()),
+                      g[f'{n}_moving_{w}'], 'moving ' + w)
+    assert_parity(B.inlet((nx, ny), 1.02, 0.1)(f_post.copy()), g[n + '_inlet'], 'inlet')
+    assert_parity(B.outlet()(f_prev.copy(), f_post.copy()), g[n + '_outlet'], 'outlet')
+    m = edge('x0') | edge('x1')
+    assert_parity(B.periodic_with_pressure_variations(m, 0.3345, 0.3321)(f_pre.copy(), rho, u), g[n + '_pbc_x'], 'pbc')
+    pm = g[n + '_plate_mask'].copy()
+    assert_parity(B.rigid_object(pm)(f_pre.copy(), f_post.copy()), g[n + '_plate'], 'plate')
+    assert np.array_equal(pm, g[n + '_plate_mask_after'])   # the reference mutates the caller's mask
+    # in-place semantics: the closure returns the array it was given
+    fp = f_post.copy()
+    assert B.rigid_wall(edge('y1'))(f_pre, fp) is fp
+    # bundles called directly
+    assert_parity(BU.couette_flow_boundary_conditions(nx, ny, 0.05, 1.0)(f_pre.copy(), f_post.copy(), rho, u, f_prev),
+                  g[n + '_couette'], 'couette bundle')
+    fpre = f_pre.copy()
+    assert_parity(BU.poiseuille_flow_boundary_conditions(nx, ny, 0.3345, 0.3321)(fpre, f_post.copy(), rho, u, f_prev),
+                  g[n + '_poiseuille'], 'poiseuille bundle')
+    assert_parity(fpre, g[n + '_poiseuille_fpre_after'], 'poiseuille f_pre after')
+
+
+def test_reference_bc_known_answers(P):
+    """The literal constants of tests/test_boundary_conditions.py:62-121."""
+    B = P.boundary_conditions
+    shape = (10, 10)
+    m = np.zeros(shape, dtype=bool)
+    m[:, -1] = True
+    out = B.moving_wall(m, np.array([2, 0]), 1)(np.ones(shape + (9,)), np.zeros(shape + (9,)))
+    assert np.allclose(out[m, 4], 1) and np.allclose(out[m, 7], 1 - 1 / 3) and np.allclose(out[m, 8], 1 + 1 / 3)
+    for i in (0, 1, 2, 3, 5, 6):
+        assert np.allclose(out[m, i], 0)
+    u = np.zeros(shape + (2,))
+    u[..., 0] = 0.1
+    b = np.zeros(shape, dtype=bool)
+    b[0, :] = True
+    b[-1, :] = True
+    out = B.periodic_with_pressure_variations(b, 1, 0.1)(np.ones(shape + (9,)), np.ones(shape), u)
+    assert np.allclose(out[0, :, 1], 1.29555) and np.allclose(out[0, :, 5], 1.073888) and np.allclose(out[0, :, 8], 1.073888)
+    assert np.allclose(out[-1, :, 3], 0.943222) and np.allclose(out[-1, :, 6], 0.9858) and np.allclose(out[-1, :, 7], 0.9858)
+    assert np.allclose(out[1:-1], 1)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# configs 1-4 (BASELINE.json) through the reference's driver loops
+# ---------------------------------------------------------------------------------------------------------
+def test_config1_shear_wave_omega_sweep(P, oracle):
+    L = P.lattice_boltzmann_method
+    g = load('shear.npz')
+    for om in (0.3, 1.0, 1.7):
+        rho, u = oracle.np.sinusoidal_velocity_x((100, 50), 0.01)
+        f = L.equilibrium_distr_func(rho, u)
+        amp = []
+        for t in range(1, 1001):
+            f, rho, u = L.lattice_boltzmann_step(f, rho, u, om)
+            if t <= 200:   # the driver's per-step whole-field reduction (experiments.py:188-193), on the device
+                vmin, vmax = np.amin(u), np.amax(u)
+                amp.append(np.abs(vmin) if np.abs(vmin) > np.abs(vmax) else np.abs(vmax))
+            if t in (1, 10, 100, 1000):
+                check_digests(g, f'v_om{om}_t{t}', f, rho, u)
+        assert np.array_equal(np.array(amp), g[f'v_om{om}_amp'][:200])
+    rho, u = oracle.np.sinusoidal_density_x((50, 50), 0.5, 0.08)
+    f = L.equilibrium_distr_func(rho, u)
+    for t in range(1, 1001):
+        f, rho, u = L.lattice_boltzmann_step(f, rho, u, 0.8)
+        if t in (1, 10, 100, 1000):
+            check_digests(g, f'd_t{t}', f, rho, u)
+
+
+def test_omega_change_between_calls(P, oracle):
+    """experiments.py:171-180 sweeps omega; the speculative collision of the resident state must be redone."""
+    L = P.lattice_boltzmann_method
+    rho, u = oracle.np.sinusoidal_velocity_x((32, 48), 0.05)
+    f = L.equilibrium_distr_func(rho, u)
+    fo, ro, uo = f.copy(), rho.copy(), u.copy()
+    omegas = [0.7, 0.7, 1.4, 1.4, 0.2, 1.9, 1.9]
+    for om in omegas:
+        f, rho, u = L.lattice_boltzmann_step(f, rho, u, om)
+        fo, ro, uo = oracle.c.run(fo, ro, uo, om, oracle.c.periodic(), 1)
+    assert_parity(f, fo, 'f')
+    assert_parity(rho, ro, 'rho')
+    assert_parity(u, uo, 'u')
+
+
+@pytest.mark.parametrize('mode', ['mask', 'edge'])
+def test_config2_couette(P, oracle, mode):
+    from lattice_boltzmann_parallel_solver_b200 import _native as N
+    from lattice_boltzmann_parallel_solver_b200.engine import Lattice
+    g = load('couette.npz')
+    lx = ly = 100
+    rho, u = oracle.np.uniform((lx, ly))
+    f = P.lattice_boltzmann_method.equilibrium_distr_func(rho, u)
+    bc = P.boundary_utils.couette_flow_boundary_conditions(lx, ly, 0.05, np.mean(rho))
+    lat = Lattice(lx, ly, bc.kind_map((lx, ly)), bc_mode=N.BC_MASK if mode == 'mask' else N.BC_EDGE)
+    lat.load(f, rho, u, 1.0)
+    t = 0
+    for tt in (1, 10, 100, 1000, 10000):
+        lat.run(tt - t)
+        t = tt
+        fo, ro, uo = lat.fields()
+        check_digests(g, f't{tt}', fo, ro, uo)
+    assert np.array_equal(uo[lx // 2, :, 0], g['ux_profile_t10000'])
+    lat.close()
+
+
+def test_config2_couette_python_loop(P, oracle):
+    g = load('couette.npz')
+    L = P.lattice_boltzmann_method
+    lx = ly = 100
+    rho, u = oracle.np.uniform((lx, ly))
+    f = L.equilibrium_distr_func(rho, u)
+    bc = P.boundary_utils.couette_flow_boundary_conditions(lx, ly, 0.05, np.mean(rho))
+    kept = []
+    for t in range(1, 101):
+        f, rho, u = L.lattice_boltzmann_step(f, rho, u, 1.0, bc)
+        if t in (1, 10):
+            kept.append((t, f, rho, u))     # experiments.py:254 keeps every step's velocity: handles must stay valid
+    check_digests(g, 't100', f, rho, u)
+    assert_parity(f, g['f100'], 'f100')
+    for t, a, b, c in kept:
+        check_digests(g, f't{t}', a, b, c)
+
+
+@pytest.mark.parametrize('mode', ['mask', 'edge'])
+def test_config3_poiseuille(P, oracle, mode):
+    from lattice_boltzmann_parallel_solver_b200 import _native as N
+    from lattice_boltzmann_parallel_solver_b200.engine import Lattice
+    g = load('poiseuille.npz')
+    lx, ly = 100, 50
+    rho, u = oracle.np.uniform((lx, ly))
+    f = P.lattice_boltzmann_method.equilibrium_distr_func(rho, u)
+    bc = P.boundary_utils.poiseuille_flow_boundary_conditions(lx, ly, float(g['p_in']), float(g['p_out']))
+    lat = Lattice(lx, ly, bc.kind_map((lx, ly)), bc_mode=N.BC_MASK if mode == 'mask' else N.BC_EDGE)
+    lat.load(f, rho, u, 1.5)
+    t = 0
+    for tt in (1, 10, 100, 1000):
+        lat.run(tt - t)
+        t = tt
+        fo, ro, uo = lat.fields()
+        check_digests(g, f't{tt}', fo, ro, uo)
+        if tt == 100:
+            assert_parity(fo, g['f100'], 'f100')
+    assert np.array_equal(uo[1, :, 0], g['ux_profile_x1'])
+    assert np.array_equal(ro[:, ly // 2], g['rho_centerline'])
+    lat.close()
+
+
+KARMAN = dict(lx=420, ly=180, d=40, u0=0.1, rho_in=1.0, nu=0.04)
+
+
+def test_config4_karman_parallel_path_1000_steps(P, oracle):
+    """The loop of experiments.py:650-704 / tests/test_parallelization_von_karman.py:18-57 on one rank: ghost ring,
+    communication(), parallel BC bundle, per-step probe read. 1000 steps; fields, ghost ring included, and the
+    probe trace must equal the reference's bit for bit (incl. its own 12-sample golden and the cluster trace)."""
+    L, BU, PU = P.lattice_boltzmann_method, P.boundary_utils, P.parallelization_utils
+    from lattice_boltzmann_parallel_solver_b200 import dist
+    g = load('karman.npz')
+    k = KARMAN
+    lx, ly = k['lx'], k['ly']
+    omega = np.reciprocal(3 * k['nu'] + 0.5)
+    comm = dist.WorldComm()
+    x_size, y_size = PU.get_xy_size(comm.Get_size())
+    cart = comm.Create_cart(dims=[x_size, y_size], periods=[True, True], reorder=False)
+    c = cart.Get_coords(comm.Get_rank())
+    nlx, nly = PU.get_local_coords(c, lx, ly, x_size, y_size)
+    rho, u = oracle.np.uniform((nlx + 2, nly + 2), 1.0, k['u0'], 0.0)
+    f = L.equilibrium_distr_func(rho, u)
+    pc, px, py = PU.global_coord_to_local_coord(c, 3 * lx // 4, ly // 2, lx, ly, x_size, y_size)
+    vel_at_p = [np.linalg.norm(u[px, py, ...])]
+    comps = [u[px, py].copy()]
+    bc = BU.parallel_von_karman_boundary_conditions(c, nlx, nly, lx, ly, x_size, y_size, k['rho_in'], k['u0'], k['d'])
+    com = PU.communication(cart)
+    for t in range(1, 1001):
+        f, rho, u = L.lattice_boltzmann_step(f, rho, u, omega, bc, com)
+        v = u[px, py, ...]
+        comps.append(np.array(v))
+        vel_at_p.append(np.linalg.norm(v))
+        if t in (1, 2, 11, 100, 1000):
+            check_digests(g, f't{t}', f, rho, u)
+            F, R, U = np.asarray(f), np.asarray(rho), np.asarray(u)
+            check_digests(g, f't{t}_int', F[1:-1, 1:-1], R[1:-1, 1:-1], U[1:-1, 1:-1])
+    assert np.array_equal(np.array(comps), g['probe_uxuy'])
+    assert np.array_equal(np.array(vel_at_p)[:12], load('ref_vel_at_p.npy'))
+    assert np.array_equal(np.array(vel_at_p), load('ref_probe_100.npy')[:1001])
+
+
+def test_config4_karman_native_run_with_probe(P, oracle):
+    """Same scenario through the native multi-step API: 1000 steps in one call, probe ring read afterwards."""
+    from lattice_boltzmann_parallel_solver_b200.engine import Lattice
+    g = load('karman.npz')
+    k = KARMAN
+    lx, ly = k['lx'], k['ly']
+    omega = float(np.reciprocal(3 * k['nu'] + 0.5))
+    rho, u = oracle.np.uniform((lx + 2, ly + 2), 1.0, k['u0'], 0.0)
+    f = P.lattice_boltzmann_method.equilibrium_distr_func(rho, u)
+    bc = P.boundary_utils.parallel_von_karman_boundary_conditions([0, 0], lx, ly, lx, ly, 1, 1, k['rho_in'], k['u0'], k['d'])
+    lat = Lattice(lx + 2, ly + 2, bc.kind_map((lx + 2, ly + 2)), ghost=(1, 1))
+    lat.connect_self_periodic()
+    lat.probe(3 * lx // 4 + 1, ly // 2 + 1, capacity=2048)
+    lat.load(f, rho, u, omega)
+    lat.run(1000)
+    trace = lat.probe_read(1, 1000)
+    assert np.array_equal(trace, g['probe_uxuy'][1:])
+    fo, ro, uo = lat.fields()
+    check_digests(g, 't1000', fo, ro, uo)
+    mn_r, mx_r, mn_u, mx_u = lat.minmax()
+    assert (mn_r, mx_r, mn_u, mx_u) == (ro.min(), ro.max(), uo.min(), uo.max())
+    lat.close()
+
+
+def test_karman_serial_rigid_object(P, oracle):
+    """milestoneQuickFunctionCalls.py:304-320 — inlet, outlet and rigid_object composed by hand, no ghost ring."""
+    L, B, BU = P.lattice_boltzmann_method, P.boundary_conditions, P.boundary_utils
+    g = load('karman_serial.npz')
+    k = KARMAN
+    lx, ly, d = k['lx'], k['ly'], k['d']
+    omega = np.reciprocal(3 * k['nu'] + 0.5)
+    plate = np.zeros((lx, ly))
+    plate[lx // 4, ly // 2 - d // 2:ly // 2 + d // 2] = 1
+    bundle = BU.BoundaryBundle('milestone_6', (lx, ly))
+    bundle.add(B.inlet((lx, ly), k['rho_in'], k['u0'])).add(B.outlet()).add(B.rigid_object(plate.astype(bool)))
+    rho, u = oracle.np.uniform((lx, ly), 1.0, k['u0'], 0.0)
+    f = L.equilibrium_distr_func(rho, u)
+    for t in range(1, 201):
+        f, rho, u = L.lattice_boltzmann_step(f, rho, u, omega, bundle)
+        if t in (1, 11, 200):
+            check_digests(g, f't{t}', f, rho, u)
+    assert_parity(np.asarray(u)[[0, 1, 105, 106, 315, 418, 419]], g['u200_rows'], 'u rows')
+
+
+# ---------------------------------------------------------------------------------------------------------
+# fuzz against the C oracle on ragged sizes and random fields
+# ---------------------------------------------------------------------------------------------------------
+def random_state(oracle, shape, seed):
+    rng = np.random.default_rng(seed)
+    rho = rng.uniform(0.9, 1.1, shape)
+    ang = rng.uniform(0, 2 * np.pi, shape)
+    mag = rng.uniform(0, 0.05, shape)
+    u = np.dstack([mag * np.cos(ang), mag * np.sin(ang)])
+    f = oracle.np.equilibrium(rho, u) * rng.uniform(0.98, 1.02, shape + (9,))   # off equilibrium
+    return f, rho, u
+
+
+@pytest.mark.parametrize('shape', [(1, 1), (1, 7), (5, 1), (2, 2), (3, 17), (37, 23), (130, 257), (64, 1024), (300, 1000)])
+def test_fuzz_periodic(P, oracle, shape):
+    from lattice_boltzmann_parallel_solver_b200.engine import Lattice
+    f, rho, u = random_state(oracle, shape, 11)
+    lat = Lattice(*shape)
+    lat.load(f, rho, u, 1.23)
+    lat.run(20)
+    got = lat.fields()
+    ref = oracle.c.run(f, rho, u, 1.23, oracle.c.periodic(), 20)
+    for a, b, n in zip(got, ref, 'f rho u'.split()):
+        assert_parity(a, b, f'{shape} {n}')
+    # sub-rectangle read
+    x0, x1 = 0, max(1, shape[0] // 2)
+    y0, y1 = shape[1] // 3, shape[1]
+    part = lat.fields(region=(x0, x1, y0, y1))
+    for a, b in zip(part, ref):
+        assert_parity(a, b[x0:x1, y0:y1], f'{shape} region')
+    lat.close()
+
+
+@pytest.mark.parametrize('shape,mode', [((24, 31), 'mask'), ((24, 31), 'edge'), ((130, 70), 'mask'), ((130, 70), 'edge')])
+def test_fuzz_scenarios(P, oracle, shape, mode):
+    from lattice_boltzmann_parallel_solver_b200 import _native as N
+    from lattice_boltzmann_parallel_solver_b200.engine import Lattice
+    BU = P.boundary_utils
+    nx, ny = shape
+    bm = N.BC_MASK if mode == 'mask' else N.BC_EDGE
+    f, rho, u = random_state(oracle, shape, 3)
+    for name in ('couette', 'poiseuille'):
+        if name == 'couette':
+            bc = BU.couette_flow_boundary_conditions(nx, ny, 0.03, 1.01)
+            sc = oracle.c.couette(0.03, 1.01)
+        else:
+            bc = BU.poiseuille_flow_boundary_conditions(nx, ny, 0.3345, 0.3321)
+            sc = oracle.c.poiseuille(0.3345, 0.3321)
+        lat = Lattice(nx, ny, bc.kind_map(shape), bc_mode=bm)
+        lat.load(f, rho, u, 0.9)
+        lat.run(30)
+        ref = oracle.c.run(f, rho, u, 0.9, sc, 30)
+        for a, b, n in zip(lat.fields(), ref, 'f rho u'.split()):
+            assert_parity(a, b, f'{name} {shape} {mode} {n}')
+        lat.close()
+    # von Karman with ghost ring
+    lx, ly = nx - 2, ny - 2
+    bc = BU.parallel_von_karman_boundary_conditions([0, 0], lx, ly, lx, ly, 1, 1, 1.0, 0.1, 8)
+    lat = Lattice(nx, ny, bc.kind_map(shape), ghost=(1, 1), bc_mode=bm)
+    lat.connect_self_periodic()
+    lat.load(f, rho, u, 1.6)
+    lat.run(30)
+    ref = oracle.c.run(f, rho, u, 1.6, oracle.c.karman(lx, ly, 1.0, 0.1, 8, ghost=1), 30)
+    for a, b, n in zip(lat.fields(), ref, 'f rho u'.split()):
+        assert_parity(a, b, f'karman {shape} {mode} {n}')
+    lat.close()
+
+
+def test_device_init_matches_upload(P, oracle):
+    from lattice_boltzmann_parallel_solver_b200.engine import Lattice
+    shape = (48, 80)
+    rho, u = oracle.np.sinusoidal_velocity_x(shape, 0.01)
+    f = oracle.np.equilibrium(rho, u)
+    a = Lattice(*shape)
+    a.load(f, rho, u, 1.1)
+    b = Lattice(*shape)
+    b.load_equilibrium(1.1, ux_y=u[0, :, 0])
+    a.run(7)
+    b.run(7)
+    for x, y in zip(a.fields(), b.fields()):
+        assert_parity(x, y, 'device init')
+    rho, u = oracle.np.sinusoidal_density_x(shape, 0.5, 0.08)
+    b.load_equilibrium(0.6, rho_x=rho[:, 0])
+    b.run(5)
+    ref = oracle.c.run(oracle.np.equilibrium(rho, u), rho, u, 0.6, oracle.c.periodic(), 5)
+    for x, y in zip(b.fields(), ref):
+        assert_parity(x, y, 'device init density')
+    a.close()
+    b.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE.json's full size through size-independent properties
+# ---------------------------------------------------------------------------------------------------------
+def test_full_size_16384_rows_equal_thin_lattice(P, oracle):
+    """The throughput workload (16384x16384 periodic shear wave) is invariant along x, so every
+    row must equal — bit for bit — the rows of a 4x16384 lattice the C oracle can run. Also: total mass is
+    conserved and the fields are exactly x-invariant."""
+    from lattice_boltzmann_parallel_solver_b200.engine import Lattice
+    n, steps = 16384, 24
+    y = np.arange(n)
+    prof = 0.01 * np.sin(np.divide(2 * np.pi * y, n))
+    lat = Lattice(n, n)
+    lat.load_equilibrium(1.0, ux_y=prof)
+    lat.run(steps)
+    rho, u = oracle.np.sinusoidal_velocity_x((4, n), 0.01)
+    assert np.array_equal(u[0, :, 0], prof)
+    ref = oracle.c.run(oracle.np.equilibrium(rho, u), rho, u, 1.0, oracle.c.periodic(), steps)
+    for x0 in (0, 1, 8191, 16380):
+        got = lat.fields(region=(x0, x0 + 4, 0, n))
+        for a, b, nm in zip(got, ref, 'f rho u'.split()):
+            assert_parity(a, b, f'rows {x0}.. {nm}')
+    mn_r, mx_r, mn_u, mx_u = lat.minmax()
+    assert mn_r == ref[1].min() and mx_r == ref[1].max() and mn_u == ref[2].min() and mx_u == ref[2].max()
+    lat.close()
