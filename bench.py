@@ -155,6 +155,10 @@ def main():
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--e2e-size', type=int, default=0, help='lattice edge of the e2e job (default: --size)')
+    ap.add_argument('--workload', default='shear', choices=['shear', 'karman'],
+                    help='shear: the headline periodic lattice; karman: inlet/outlet/plate rule set scaled to the same '
+                         'lattice (single GPU; evidence for the flag-mask vs edge-kernel choice)')
+    ap.add_argument('--bc-mode', default='auto', choices=['auto', 'mask', 'edge'])
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
@@ -186,13 +190,20 @@ def main():
         if world > 1:
             dist.barrier()
 
-    if world == 1:
+    if args.workload == 'karman':
+        assert world == 1, 'the BC-bearing comparison is a single-GPU measurement'
+        lat = karman_lattice(nx_local, ny, {'auto': N.BC_AUTO, 'mask': N.BC_MASK, 'edge': N.BC_EDGE}[args.bc_mode])
+        args.no_e2e = True
+    elif world == 1:
         lat = Lattice(nx_local, ny)
     else:
         lat = Lattice(nx_local + 2, ny, ghost=(1, 0))
         cart = ldist.comm_world().Create_cart(dims=[world, 1], periods=[True, True])
         par.communication(cart).attach(lat)
-    lat.load_equilibrium(OMEGA, ux_y=prof)
+    if args.workload == 'karman':
+        lat.load_equilibrium(float(np.reciprocal(3 * 0.04 + 0.5)), rho0=1.0, ux0=0.1)
+    else:
+        lat.load_equilibrium(OMEGA, ux_y=prof)
     barrier()
 
     stream = torch.cuda.ExternalStream(lat.stream)
@@ -258,13 +269,26 @@ def main():
             'metric': 'D2Q9 fp64 MLUPS', 'value': mlups, 'unit': 'MLUPS', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
             'scaling': 'strong' if args.strong else 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': workload_config(args, world), 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
+            'config': dict(workload_config(args, world), **({'workload': f'von Karman rule set (inlet, outlet, plate) on {args.size}x{args.size}, bc_mode={args.bc_mode}'} if args.workload == 'karman' else {})), 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
             'roofline': roofline, 'cpu_baseline': cpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def karman_lattice(nx, ny, bc_mode):
+    """milestone_6's rule set (inlet column, outlet column, thin plate of ny/4.5 at nx/4) on an nx x ny lattice."""
+    from lattice_boltzmann_parallel_solver_b200 import boundary_conditions as B
+    from lattice_boltzmann_parallel_solver_b200 import boundary_utils as BU
+    from lattice_boltzmann_parallel_solver_b200.engine import Lattice
+    d = int(ny / 4.5) // 2 * 2
+    plate = np.zeros((nx, ny), dtype=bool)
+    plate[nx // 4, ny // 2 - d // 2:ny // 2 + d // 2] = True
+    bundle = BU.BoundaryBundle('von_karman_serial', (nx, ny))
+    bundle.add(B.inlet((nx, ny), 1.0, 0.1)).add(B.outlet()).add(B.rigid_object(plate))
+    return Lattice(nx, ny, bundle.kind_map((nx, ny)), bc_mode=bc_mode)
 
 
 def run_e2e(args, lat, world, rank, nx_local, ny, prof, barrier):

@@ -193,7 +193,7 @@ __device__ __noinline__ void store_pbc(const StepParams &P, unsigned flags, int 
 
 // communication() (parallelization_utils.py:34-49) without the copy: an interior cell on the edge of the block
 // also writes its nine post-collision populations into the ghost cell(s) of the neighbour(s) that mirror it.
-__device__ __noinline__ void store_halo(const StepParams &P, int x, int y, const double (&s)[9])
+__device__ __forceinline__ void store_halo(const StepParams &P, int x, int y, const double (&s)[9])
 {
     const int ex_lo = (P.gx && x == P.gx), ex_hi = (P.gx && x == P.NX - 1 - P.gx);
     const int ey_lo = (P.gy && y == P.gy), ey_hi = (P.gy && y == P.NY - 1 - P.gy);
@@ -265,6 +265,56 @@ __device__ __forceinline__ void halo_signal(const StepParams &P)
 //   FINAL: stop after the moments and write reference-layout f_post / rho / u (materialize)
 //   LIST : cells come from a compact list (edge fix-up kernel) instead of a row range
 // -------------------------------------------------------------------------------------------------------
+// Everything one cell does after its nine f_post values are known (shared by the register-resident fluid path
+// and the out-of-line rule path).
+template <bool HALO, bool FINAL>
+__device__ __forceinline__ void finish_cell(const StepParams &P, int x, int y, const double (&f)[9], unsigned flags,
+                                            unsigned skip)
+{
+    double rho, ux, uy;
+    moments(f, rho, ux, uy);
+    if (FINAL) {
+        const long long o = (long long)(x - P.ox0) * P.ow + (y - P.oy0);
+        if (P.o_f) {
+#pragma unroll
+            for (int i = 0; i < 9; i++) P.o_f[o * 9 + i] = f[i];
+        }
+        if (P.o_rho) P.o_rho[o] = rho;
+        if (P.o_u) {
+            P.o_u[o * 2] = ux;
+            P.o_u[o * 2 + 1] = uy;
+        }
+        return;
+    }
+    if (P.probe_slot && x == P.px && y == P.py) {
+        P.probe_slot[0] = ux;
+        P.probe_slot[1] = uy;
+    }
+    double p[9], e[9], s[9];
+    eq_poly(ux, uy, p);
+    eq_from_poly(rho, p, e);
+    collide(f, e, P.omega, s);
+    if (flags & LBM_CELL_OUTLET_SRC) {
+        P.out_next[0 * P.pitch + y] = f[3];
+        P.out_next[1 * P.pitch + y] = f[6];
+        P.out_next[2 * P.pitch + y] = f[7];
+    }
+    store_cell(P, x, y, s, skip);
+    if (flags & (LBM_CELL_PBC_IN_SRC | LBM_CELL_PBC_OUT_SRC)) store_pbc(P, flags, y, s, p, e);
+    if (HALO) store_halo(P, x, y, s);
+}
+
+// A non-fluid cell, entirely out of line: its private f[9] may live in local memory without dragging the
+// fluid path's registers there (the first version shared one array and doubled the DRAM writes).
+template <bool HALO, bool FINAL>
+__device__ __noinline__ void rule_cell(const StepParams &P, int x, int y, unsigned kind)
+{
+    const lbm_kind k = P.kinds[kind];
+    double f[9];
+    pull_rules(P, k, x, y, f);
+    finish_cell<HALO, FINAL>(P, x, y, f, k.flags, k.skip_store);
+}
+
 template <bool MASK, bool HALO, bool FINAL, bool LIST>
 __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepParams P)
 {
@@ -284,52 +334,14 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepParams
         active = y < P.y1;
     }
     if (active) {
-        double f[9];
-        unsigned flags = 0, skip = 0;
-        bool fluid = true;
-        if (MASK || LIST) {
-            const unsigned kind = P.kind_map[(long long)x * P.pitch + y];
-            if (kind != 0) {
-                fluid = false;
-                const lbm_kind k = P.kinds[kind];
-                flags = k.flags;
-                skip = k.skip_store;
-                pull_rules(P, k, x, y, f);
-            }
-        }
-        if (fluid) pull_fluid(P, x, y, f);
-
-        double rho, ux, uy;
-        moments(f, rho, ux, uy);
-
-        if (FINAL) {
-            const long long o = (long long)(x - P.ox0) * P.ow + (y - P.oy0);
-            if (P.o_f) {
-#pragma unroll
-                for (int i = 0; i < 9; i++) P.o_f[o * 9 + i] = f[i];
-            }
-            if (P.o_rho) P.o_rho[o] = rho;
-            if (P.o_u) {
-                P.o_u[o * 2] = ux;
-                P.o_u[o * 2 + 1] = uy;
-            }
+        unsigned kind = 0;
+        if (MASK || LIST) kind = P.kind_map[(long long)x * P.pitch + y];
+        if (kind != 0) {
+            rule_cell<HALO, FINAL>(P, x, y, kind);
         } else {
-            if (P.probe_slot && x == P.px && y == P.py) {
-                P.probe_slot[0] = ux;
-                P.probe_slot[1] = uy;
-            }
-            double p[9], e[9], s[9];
-            eq_poly(ux, uy, p);
-            eq_from_poly(rho, p, e);
-            collide(f, e, P.omega, s);
-            if ((MASK || LIST) && (flags & LBM_CELL_OUTLET_SRC)) {
-                P.out_next[0 * P.pitch + y] = f[3];
-                P.out_next[1 * P.pitch + y] = f[6];
-                P.out_next[2 * P.pitch + y] = f[7];
-            }
-            store_cell(P, x, y, s, skip);
-            if ((MASK || LIST) && (flags & (LBM_CELL_PBC_IN_SRC | LBM_CELL_PBC_OUT_SRC))) store_pbc(P, flags, y, s, p, e);
-            if (HALO) store_halo(P, x, y, s);
+            double f[9];
+            pull_fluid(P, x, y, f);
+            finish_cell<HALO, FINAL>(P, x, y, f, 0u, 0u);
         }
     }
     if (HALO && !FINAL) halo_signal(P);

@@ -202,6 +202,21 @@ class Lattice:
                    for h in handles)
 
 
+def connect_blocks(blocks, dims):
+    """Wire a whole periodic Cartesian topology of lattices that live in THIS process (one per block coordinate,
+    possibly on different GPUs): blocks[(cx, cy)] -> Lattice, dims = (x_size, y_size). The multi-process equivalent
+    is `parallelization_utils.communication(comm).attach(lattice)`."""
+    xs, ys = int(dims[0]), int(dims[1])
+    exports = {c: lat.halo_export() for c, lat in blocks.items()}
+    for (cx, cy), lat in blocks.items():
+        for dx in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                if (dx == 0 and dy == 0) or (dx and not lat.ghost[0]) or (dy and not lat.ghost[1]):
+                    continue
+                lat.halo_connect((dx + 1) * 3 + dy + 1, exports[((cx + dx) % xs, (cy + dy) % ys)])
+        lat.halo_finalize()
+
+
 _SHAPES = {'f': lambda nx, ny: (nx, ny, 9), 'rho': lambda nx, ny: (nx, ny), 'u': lambda nx, ny: (nx, ny, 2)}
 
 

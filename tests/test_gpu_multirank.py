@@ -1,0 +1,120 @@
+"""k-rank decompositions on the GPU: (a) all k blocks as k device lattices of ONE process (runs on a 1-GPU box;
+exercises the ghost stores, the 8-neighbour wiring and the step-flag protocol between distinct contexts), and
+(b) real one-process-per-GPU runs under torchrun with CUDA-IPC peer stores (needs >= 2 GPUs).
+Reference design: tests/test_parallelization_von_karman.py under `mpirun -N {1,2,4,6,8,9,14}` (.travis.yml:20-26):
+the parallel run must equal the serial one; here additionally every rank's whole local array, ghost ring
+included, must equal what the reference itself produced on k ranks (tests/golden/karman_ranks.npz)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from tests.helpers import sha
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+KARMAN = dict(lx=420, ly=180, d=40, u0=0.1, rho_in=1.0, nu=0.04)
+
+
+def _gpu_count():
+    from lattice_boltzmann_parallel_solver_b200 import _native as N
+    return N.load().lbm_device_count()
+
+
+@pytest.mark.parametrize('size', [2, 4, 6, 8, 9, 14])
+def test_k_blocks_in_one_process(size):
+    import lattice_boltzmann_parallel_solver_b200 as P
+    from lattice_boltzmann_parallel_solver_b200.engine import Lattice, connect_blocks
+    from oracle import lbm_numpy as onp
+    PU, BU, L = P.parallelization_utils, P.boundary_utils, P.lattice_boltzmann_method
+    g = np.load(os.path.join(GOLDEN, 'karman_ranks.npz'))
+    k = KARMAN
+    lx, ly = k['lx'], k['ly']
+    omega = float(np.reciprocal(3 * k['nu'] + 0.5))
+    x_size, y_size = PU.get_xy_size(size)
+    xs, ys = int(x_size), int(y_size)
+    ndev = _gpu_count()
+    blocks, init = {}, {}
+    for cx in range(xs):
+        for cy in range(ys):
+            c = [cx, cy]
+            nlx, nly = PU.get_local_coords(c, lx, ly, x_size, y_size)
+            bc = BU.parallel_von_karman_boundary_conditions(c, nlx, nly, lx, ly, x_size, y_size, k['rho_in'], k['u0'], k['d'])
+            blocks[(cx, cy)] = Lattice(nlx + 2, nly + 2, bc.kind_map((nlx + 2, nly + 2)), ghost=(1, 1),
+                                       device=(cx * ys + cy) % ndev)
+            rho, u = onp.uniform((nlx + 2, nly + 2), 1.0, k['u0'], 0.0)
+            init[(cx, cy)] = (L.equilibrium_distr_func(rho, u), rho, u)
+    connect_blocks(blocks, (xs, ys))
+    for c, lat in blocks.items():
+        lat.load(*init[c], omega)
+    for lat in blocks.values():
+        lat.sync()
+    for _ in range(11):
+        for lat in blocks.values():
+            lat.run(1)
+    G = np.zeros((lx, ly, 9))
+    for (cx, cy), lat in blocks.items():
+        lat.sync()
+        f, rho, u = lat.fields()
+        r = cx * ys + cy
+        assert sha(f) == str(g[f'n{size}_r{r}_f_full']), f'rank {r} f (ghost ring included)'
+        assert sha(rho) == str(g[f'n{size}_r{r}_rho_full']), f'rank {r} rho'
+        assert sha(u) == str(g[f'n{size}_r{r}_u_full']), f'rank {r} u'
+        x0, y0 = cx * (lx // xs), cy * (ly // ys)
+        G[x0:x0 + f.shape[0] - 2, y0:y0 + f.shape[1] - 2] = f[1:-1, 1:-1]
+    assert sha(G) == str(g['serial_f11'])
+    for lat in blocks.values():
+        lat.close()
+
+
+def test_slabs_equal_single_block():
+    """The bench decomposition (1-D slabs along x, ghost rows only, in-kernel periodic wrap along y, split edge /
+    interior launches on two streams) must give exactly the single-block result."""
+    from lattice_boltzmann_parallel_solver_b200.engine import Lattice, connect_blocks
+    from oracle import lbm_c, lbm_numpy as onp
+    nx, ny, k, steps = 4096, 512, 4, 12          # 2M cells: above the threshold that enables the split launch
+    rho, u = onp.sinusoidal_velocity_x((nx, ny), 0.01)
+    rng = np.random.default_rng(2)
+    rho = rho * rng.uniform(0.99, 1.01, rho.shape)    # break the x-invariance so that halo errors are visible
+    f = onp.equilibrium(rho, u)
+    ref = lbm_c.run(f, rho, u, 1.1, lbm_c.periodic(), steps)
+    ndev = _gpu_count()
+    n = nx // k
+    blocks = {}
+    for c in range(k):
+        lat = Lattice(n + 2, ny, ghost=(1, 0), device=c % ndev)
+        blocks[(c, 0)] = lat
+    connect_blocks(blocks, (k, 1))
+
+    def padded(a, c):
+        idx = np.arange(c * n - 1, (c + 1) * n + 1) % nx
+        return np.ascontiguousarray(a[idx])
+    for c in range(k):
+        blocks[(c, 0)].load(padded(f, c), padded(rho, c), padded(u, c), 1.1)
+    for lat in blocks.values():
+        lat.sync()
+    for _ in range(steps):
+        for lat in blocks.values():
+            lat.run(1)
+    for c in range(k):
+        lat = blocks[(c, 0)]
+        lat.sync()
+        got = lat.fields(region=(1, n + 1, 0, ny))
+        for a, b, nm in zip(got, ref, 'f rho u'.split()):
+            assert np.array_equal(a, b[c * n:(c + 1) * n]), f'slab {c} {nm}'
+        lat.close()
+
+
+@pytest.mark.multigpu
+@pytest.mark.parametrize('size', [2, 4, 8])
+def test_one_process_per_gpu_torchrun(size):
+    if _gpu_count() < size:
+        pytest.skip(f'needs {size} GPUs')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={size}',
+           '--master-addr', '127.0.0.1', '--master-port', str(29500 + size), os.path.join(ROOT, 'tests', 'mp_karman.py')]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert f'OK {size} ranks' in res.stdout

@@ -1,0 +1,206 @@
+"""CPU-only tests of the host side: C-ABI surface, topology math, boundary compilation, the process-group
+communicator over gloo (world_size 2 and 4), failure modes without a GPU."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def test_library_exports_every_declared_symbol():
+    """include/lbm_b200.h <-> liblbm_b200.so <-> the ctypes table, no compute call."""
+    from lattice_boltzmann_parallel_solver_b200 import _native as N
+    header = open(os.path.join(ROOT, 'include', 'lbm_b200.h')).read()
+    declared = set(re.findall(r'\b(lbm_[a-z_0-9]+)\s*\(', header))
+    declared -= {'lbm_ctx', 'lbm_kind', 'lbm_bc_desc', 'lbm_halo_export'}
+    assert declared == set(N.SIGNATURES), declared ^ set(N.SIGNATURES)
+    lib = N.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b'sm_100a' in lib.lbm_version()
+    assert ctypes.sizeof(N.Kind) == 12 and ctypes.sizeof(N.HaloExport) == 104
+
+
+def test_no_gpu_means_loud_failure():
+    from lattice_boltzmann_parallel_solver_b200 import _native as N
+    if N.load().lbm_device_count() > 0:
+        pytest.skip('a GPU is visible')
+    import lattice_boltzmann_parallel_solver_b200.lattice_boltzmann_method as L
+    with pytest.raises(N.LbmNativeError):
+        L.compute_density(np.ones((4, 4, 9)))
+    with pytest.raises(N.LbmNativeError):
+        L.lattice_boltzmann_step(np.ones((4, 4, 9)), np.ones((4, 4)), np.zeros((4, 4, 2)), 1.0)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'lattice_boltzmann_parallel_solver_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', src, re.M), fn
+                assert 'liblbm_oracle' not in src, fn
+
+
+def test_topology_vs_reference_tables():
+    from lattice_boltzmann_parallel_solver_b200 import parallelization_utils as PU
+    with open(os.path.join(GOLDEN, 'topology.json')) as fh:
+        g = json.load(fh)
+    for n, v in g['get_xy_size'].items():
+        if v is None:
+            with pytest.raises(Exception, match='prime'):
+                PU.get_xy_size(int(n))
+        else:
+            xs, ys = PU.get_xy_size(int(n))
+            assert (float(xs), float(ys)) == (v[0], v[1]) and type(xs).__name__ == v[2]
+    for n, lx, ly, cx, cy, nlx, nly in g['local_coords']:
+        xs, ys = PU.get_xy_size(n)
+        assert PU.get_local_coords([cx, cy], lx, ly, xs, ys) == (nlx, nly)
+    for n, lx, ly, cx, cy, gx, gy, xin, yin, lxx, lyy, loc in g['in_process']:
+        xs, ys = PU.get_xy_size(n)
+        c = [cx, cy]
+        assert bool(PU.x_in_process(c, gx, lx, xs)) == xin and bool(PU.y_in_process(c, gy, ly, ys)) == yin
+        assert PU.global_to_local_direction(cx, gx, lx, xs) == lxx
+        assert PU.global_to_local_direction(cy, gy, ly, ys) == lyy
+        r = PU.global_coord_to_local_coord(c, gx, gy, lx, ly, xs, ys)
+        assert (None if r[0] is None else [r[1], r[2]]) == loc
+    from lattice_boltzmann_parallel_solver_b200 import lattice_boltzmann_method as L
+    assert float(L.reynolds_number(40, 0.1, 0.04)) == g['reynolds']
+    assert float(L.strouhal_number(1.1308e-3, 40, 0.1)) == g['strouhal']
+    assert np.array_equal(L.get_velocity_sets(), np.array([[0, 0], [1, 0], [0, 1], [-1, 0], [0, -1], [1, 1], [-1, 1], [-1, -1], [1, -1]]))
+    assert np.array_equal(L.vel_to_opp_vel_mapping(), [0, 3, 4, 1, 2, 7, 8, 5, 6])
+    assert np.array_equal(L.get_w_i(), [4 / 9] + [1 / 9] * 4 + [1 / 36] * 4)
+
+
+def _rules_from_oracle(bc_factory, shape, n_args):
+    """Derive the per-slot overwrite table of an ORACLE boundary closure by probing it with marker arrays, to
+    compare with the kind map this package compiles for the same scenario."""
+    nx, ny = shape
+    idx = np.arange(nx * ny * 9, dtype=np.float64).reshape(nx, ny, 9)
+    pre, post, prev = idx + 1e7, idx + 2e7, idx + 3e7
+    out = bc_factory(pre.copy(), post.copy(), np.ones(shape), np.zeros(shape + (2,)), prev.copy())
+    return out, pre, post, prev
+
+
+def test_boundary_bundles_compile_to_the_oracles_overwrites():
+    """Without a GPU: the compiled kind map must describe exactly the overwrites the oracle's closures perform
+    (which slots, from where), for Couette, the serial plate and every rank of the 2x3 and 2x7 parallel layouts."""
+    from lattice_boltzmann_parallel_solver_b200 import _native as N
+    from lattice_boltzmann_parallel_solver_b200 import boundary_spec as S
+    from lattice_boltzmann_parallel_solver_b200 import boundary_utils as BU
+    from lattice_boltzmann_parallel_solver_b200 import parallelization_utils as PU
+    from lattice_boltzmann_parallel_solver_b200.boundary_conditions import BoundaryOp
+    from oracle import lbm_numpy as onp
+    # inlet constants come from the GPU in the product; patch them with the oracle's for this CPU-only test
+    import lattice_boltzmann_parallel_solver_b200.boundary_conditions as B
+
+    def check(km, oracle_bc, shape):
+        out, pre, post, prev = _rules_from_oracle(oracle_bc, shape, 5)
+        t = km.table
+        for x in range(shape[0]):
+            for y in range(shape[1]):
+                rules, flags, skip = t.kinds[int(km.map[x, y])]
+                for i in range(9):
+                    typ, row = rules[i] & 7, rules[i] >> 3
+                    got = out[x, y, i]
+                    if typ == N.RULE_PULL:
+                        assert got == post[x, y, i], (x, y, i)
+                    elif typ == N.RULE_BOUNCE:
+                        assert got == pre[x, y, S.OPP[i]] - t.k_rows[row][S.OPP[i]], (x, y, i)
+                    elif typ == N.RULE_OUTLET:
+                        assert got == prev[x - 1, y, i], (x, y, i)
+                    else:
+                        assert got == t.c_rows[row][i], (x, y, i)
+
+    real_eq = B.equilibrium_distr_func
+    B.equilibrium_distr_func = lambda rho, u: onp.equilibrium(rho, u)
+    try:
+        shape = (12, 9)
+        check(BU.couette_flow_boundary_conditions(*shape, 0.05, 1.0).kind_map(shape), onp.couette_bc(*shape, 0.05, 1.0), shape)
+        lx, ly, d = 40, 30, 8
+        for size in (1, 6, 14):
+            xs, ys = PU.get_xy_size(size)
+            for cx in range(int(xs)):
+                for cy in range(int(ys)):
+                    c = [cx, cy]
+                    nlx, nly = PU.get_local_coords(c, lx, ly, xs, ys)
+                    shp = (nlx + 2, nly + 2)
+                    km = BU.parallel_von_karman_boundary_conditions(c, nlx, nly, lx, ly, xs, ys, 1.0, 0.1, d).kind_map(shp)
+                    check(km, onp.karman_parallel_bc(c, nlx, nly, lx, ly, int(xs), int(ys), 1.0, 0.1, d), shp)
+                    assert not km.map[0].any() and not km.map[-1].any() and not km.map[:, 0].any() and not km.map[:, -1].any()
+        # serial plate through rigid_object
+        shape = (24, 20)
+        plate = np.zeros(shape, dtype=bool)
+        plate[6, 6:14] = True
+        b = BU.BoundaryBundle('m6', shape).add(B.inlet(shape, 1.0, 0.1)).add(B.outlet()).add(B.rigid_object(plate))
+        check(b.kind_map(shape), onp.karman_serial_bc(24, 20, 1.0, 0.1, 8), shape)
+        # the split outlet is refused exactly like the reference (boundary_utils.py:174-176)
+        with pytest.raises(NotImplementedError):
+            BU.parallel_von_karman_boundary_conditions([20, 0], 1, 30, 21, 30, 21, 1, 1.0, 0.1, 8)
+        # Poiseuille: flags on rows 1 / -2, skipped stores on the virtual rows, bounce on both walls
+        km = BU.poiseuille_flow_boundary_conditions(10, 6, 0.3345, 0.3321).kind_map((10, 6))
+        t = km.table
+        assert t.rho_in == float(np.divide(0.3345, onp.CS2)) and t.rho_out == float(np.divide(0.3321, onp.CS2))
+        for y in range(6):
+            assert t.kinds[km.map[8, y]][1] & N.CELL_PBC_IN_SRC and t.kinds[km.map[1, y]][1] & N.CELL_PBC_OUT_SRC
+            assert t.kinds[km.map[0, y]][2] == (1 << 1) | (1 << 5) | (1 << 8)
+            assert t.kinds[km.map[9, y]][2] == (1 << 3) | (1 << 6) | (1 << 7)
+        for x in range(10):
+            assert [r & 7 for r in t.kinds[km.map[x, 0]][0]][2] == N.RULE_BOUNCE      # f_post[.,2] <- f_pre[.,4] at y=0
+            assert [r & 7 for r in t.kinds[km.map[x, 5]][0]][4] == N.RULE_BOUNCE
+        assert isinstance(b.ops[0][0], BoundaryOp)
+    finally:
+        B.equilibrium_distr_func = real_eq
+
+
+def test_unknown_boundary_callable_is_rejected():
+    from lattice_boltzmann_parallel_solver_b200 import lattice_boltzmann_method as L
+    with pytest.raises(TypeError, match='no CPU fallback'):
+        L._resolve_boundary(lambda *a: a[1], (4, 4))
+
+
+def test_pressure_periodic_y_variant_is_refused():
+    from lattice_boltzmann_parallel_solver_b200 import boundary_conditions as B
+    m = np.zeros((6, 6), dtype=bool)
+    m[:, 0] = True
+    m[:, -1] = True
+    m[0, 1] = True
+    op = B.periodic_with_pressure_variations(m, 0.3345, 0.3321)
+    with pytest.raises(NotImplementedError):
+        op(np.ones((6, 6, 9)), np.ones((6, 6)), np.zeros((6, 6, 2)))
+    with pytest.raises(AssertionError):
+        B.rigid_wall(np.zeros((4, 4)))           # non-bool mask, boundary_conditions.py:89
+
+
+@pytest.mark.parametrize('size', [2, 4])
+def test_gloo_ranks_host_path(size):
+    """world_size > 1 over gloo on the CPU: CartComm (coords/Shift/Sendrecv), communication(f) on host arrays,
+    the per-rank bundles' geometry and the save_mpiio gather, against the reference's own k-rank results."""
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={size}',
+           '--master-addr', '127.0.0.1', '--master-port', str(29620 + size), os.path.join(ROOT, 'tests', 'mp_karman.py'),
+           '--host']
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES='', OMP_NUM_THREADS='1')
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert f'OK {size} ranks (host/gloo)' in res.stdout
+
+
+def test_cart_comm_matches_mpi_cart_semantics():
+    from lattice_boltzmann_parallel_solver_b200 import dist
+    w = dist.WorldComm()
+    assert w.Get_size() == 1 and w.Get_rank() == 0
+    cart = w.Create_cart(dims=[1, 1], periods=[True, True], reorder=False)
+    assert cart.Get_coords(0) == [0, 0] and cart.Shift(0, 1) == (0, 0) and cart.Shift(1, -1) == (0, 0)
+    f = np.arange(6 * 5 * 9, dtype=np.float64).reshape(6, 5, 9)
+    from lattice_boltzmann_parallel_solver_b200 import parallelization_utils as PU
+    from oracle import lbm_numpy as onp
+    assert np.array_equal(PU.communication(cart)(f.copy()), onp.self_exchange(f.copy()))
+    with pytest.raises(AssertionError):
+        w.Create_cart(dims=[2, 1])
