@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'liblbm_b200.so')
+LIB_PATH = os.environ.get('LBM_B200_LIB') or os.path.join(HERE, 'liblbm_b200.so')
 
 LBM_OK, LBM_ERR_ARG, LBM_ERR_CUDA, LBM_ERR_STATE, LBM_ERR_NOMEM, LBM_ERR_TIMEOUT = range(6)
 

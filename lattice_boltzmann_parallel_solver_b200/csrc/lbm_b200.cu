@@ -126,31 +126,41 @@ __device__ __forceinline__ void pull_fluid(const StepParams &P, int x, int y, do
     f[8] = ldS(rm + 8 * pl + yp);
 }
 
-// f_post of a non-fluid cell, population by population (rule table of include/lbm_b200.h)
-__device__ __noinline__ void pull_rules(const StepParams &P, const lbm_kind &k, int x, int y, double (&f)[9])
+// f_post[I] of a non-fluid cell by its rule (rule table of include/lbm_b200.h). I is a compile-time index so that
+// the nine results stay in registers: no out-of-line call, no local-memory array anywhere in the step kernels.
+template <int I>
+__device__ __forceinline__ double pull_rule(const StepParams &P, const lbm_kind &k, int x, int y)
 {
+    constexpr int cx[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1}, cy[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
+    constexpr int opp[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
     const long long pl = P.plane;
-#pragma unroll 1
-    for (int i = 0; i < 9; i++) {
-        const int r = k.rule[i], type = r & 7, row = r >> 3;
-        double v;
-        if (type == LBM_RULE_PULL) {
-            int xs = x - kCx[i], ys = y - kCy[i];
-            xs = xs < 0 ? P.NX - 1 : (xs >= P.NX ? 0 : xs);
-            ys = ys < 0 ? P.NY - 1 : (ys >= P.NY ? 0 : ys);
-            v = ldS(P.src + i * pl + (long long)xs * P.pitch + ys);
-        } else if (type == LBM_RULE_BOUNCE) {
-            const int d = kOpp[i];
-            v = ldS(P.src + d * pl + (long long)x * P.pitch + y);
-            if (row) v = sub(v, P.ktab[row * 9 + d]);
-        } else if (type == LBM_RULE_CONST) {
-            v = P.ctab[row * 9 + i];
-        } else {  // LBM_RULE_OUTLET: i in (3,6,7) -> slot 0,1,2
-            const int slot = i == 3 ? 0 : (i == 6 ? 1 : 2);
-            v = P.out_cur[slot * P.pitch + y];
-        }
-        f[i] = v;
+    const int r = k.rule[I], type = r & 7, row = r >> 3;
+    if (type == LBM_RULE_PULL) {
+        int xs = x - cx[I], ys = y - cy[I];
+        xs = xs < 0 ? P.NX - 1 : (xs >= P.NX ? 0 : xs);
+        ys = ys < 0 ? P.NY - 1 : (ys >= P.NY ? 0 : ys);
+        return ldS(P.src + I * pl + (long long)xs * P.pitch + ys);
     }
+    if (type == LBM_RULE_BOUNCE) {
+        const double v = ldS(P.src + opp[I] * pl + (long long)x * P.pitch + y);
+        return row ? sub(v, P.ktab[row * 9 + opp[I]]) : v;
+    }
+    if (type == LBM_RULE_CONST) return P.ctab[row * 9 + I];
+    // LBM_RULE_OUTLET: populations 3, 6, 7 -> slots 0, 1, 2 of the side buffer
+    return P.out_cur[(I == 3 ? 0 : (I == 6 ? 1 : 2)) * P.pitch + y];
+}
+
+__device__ __forceinline__ void pull_rules(const StepParams &P, const lbm_kind &k, int x, int y, double (&f)[9])
+{
+    f[0] = pull_rule<0>(P, k, x, y);
+    f[1] = pull_rule<1>(P, k, x, y);
+    f[2] = pull_rule<2>(P, k, x, y);
+    f[3] = pull_rule<3>(P, k, x, y);
+    f[4] = pull_rule<4>(P, k, x, y);
+    f[5] = pull_rule<5>(P, k, x, y);
+    f[6] = pull_rule<6>(P, k, x, y);
+    f[7] = pull_rule<7>(P, k, x, y);
+    f[8] = pull_rule<8>(P, k, x, y);
 }
 
 // Everything after the collision: stores of S' (own cell, PBC-owned virtual cells, neighbours' ghosts)
@@ -171,7 +181,7 @@ __device__ __forceinline__ void store_cell(const StepParams &P, int x, int y, co
 // periodic_with_pressure_variations (boundary_conditions.py:337-344): the cell on row -2 (resp. 1) produces the
 // pre-streaming populations of the virtual node on row 0 (resp. -1) for the NEXT step:
 //   feq_d(rho_b, u) + (f_pre_d - feq_d(rho, u)),  f_pre_d = the value just collided (s), u/rho this cell's moments
-__device__ __noinline__ void store_pbc(const StepParams &P, unsigned flags, int y, const double (&s)[9],
+__device__ __forceinline__ void store_pbc(const StepParams &P, unsigned flags, int y, const double (&s)[9],
                                        const double (&p)[9], const double (&e)[9])
 {
     const long long pl = P.plane;
@@ -304,10 +314,11 @@ __device__ __forceinline__ void finish_cell(const StepParams &P, int x, int y, c
     if (HALO) store_halo(P, x, y, s);
 }
 
-// A non-fluid cell, entirely out of line: its private f[9] may live in local memory without dragging the
-// fluid path's registers there (the first version shared one array and doubled the DRAM writes).
+// A non-fluid cell. Everything is inlined with compile-time population indices: the first version called an
+// out-of-line rule interpreter through an array reference, which put f[9] of EVERY cell in local memory and
+// doubled the DRAM writes of the mask kernel (profiles/r01_summary.md).
 template <bool HALO, bool FINAL>
-__device__ __noinline__ void rule_cell(const StepParams &P, int x, int y, unsigned kind)
+__device__ __forceinline__ void rule_cell(const StepParams &P, int x, int y, unsigned kind)
 {
     const lbm_kind k = P.kinds[kind];
     double f[9];
