@@ -153,7 +153,13 @@ int lbm_minmax(lbm_ctx *ctx, int x0, int x1, int y0, int y1, double out[4]);
 /* ---------------------------------------------------------------------------------------------------------
  * Halo exchange (replaces communication(), src/parallelization_utils.py:6-52). Ghost cells of a neighbour
  * are written DIRECTLY by the kernel that computes the edge cells (peer stores over NVLink through a CUDA-IPC
- * mapping), ordered by step flags in peer memory; there is no separate copy or pack step.
+ * mapping); there is no separate copy or pack step. Ordering: the last block of every ghost-storing kernel of
+ * step n publishes "done n" into each remote neighbour's flag word; a ghost-touching kernel of step n+1 first
+ * waits until all its remote neighbours are done with n. All ranks must therefore call lbm_step in lockstep
+ * (same n_steps), as MPI ranks call Sendrecv in lockstep; ranks may drift by at most one step. A neighbour that
+ * never arrives makes the wait time out (LBM_HALO_TIMEOUT_S, default 30 s): lbm_sync then returns
+ * LBM_ERR_TIMEOUT. Loads (lbm_upload / lbm_init_equilibrium) also store ghosts: bracket them with a
+ * process-group barrier on both sides.
  * Neighbour slot index = (dx+1)*3 + (dy+1), dx,dy in {-1,0,1}, (0,0) unused.
  * ------------------------------------------------------------------------------------------------------- */
 #define LBM_IPC_HANDLE_BYTES 64

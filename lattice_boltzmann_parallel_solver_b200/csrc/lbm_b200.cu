@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -89,6 +90,9 @@ struct StepParams {
     int ox0, oy0, ow;          // ow = oy1 - oy0
     // halo
     HaloTarget halo[9];
+    // ghost snapshot (see snapshot_ghosts): [2][9][pitch] for rows 0 / NX-1, [2][9][NX] for columns 0 / NY-1
+    double *snap_row, *snap_col;
+    int use_snap;              // FINAL launches: read ghost cells from the snapshot instead of S
     // fix-up list
     const int2 *cells;
     int n_cells;
@@ -96,6 +100,7 @@ struct StepParams {
     volatile unsigned *flag_in;     // [9] in my arena: neighbour slot s finished writing my ghosts of step value
     unsigned *flag_out[9];          // neighbour's flag_in[opposite slot] (peer memory) or null
     unsigned wait_value, signal_value;
+    long long timeout_cycles;
     unsigned *done_counter;         // last-block-done counter
     unsigned *err_flag;
     int n_blocks;
@@ -105,6 +110,45 @@ struct StepParams {
 // per-cell pieces shared by all kernels
 // -------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double ldS(const double *p) { return __ldcg(p); }   // L2-coherent (peer-written ghosts)
+
+// Source value S[i][xs][ys]; materialisation launches take ghost cells from the snapshot (see snapshot_ghosts).
+__device__ __forceinline__ double ld_cell(const StepParams &P, int i, int xs, int ys)
+{
+    if (P.use_snap) {
+        if (P.gx && (xs == 0 || xs == P.NX - 1)) return P.snap_row[((xs ? 1 : 0) * 9 + i) * (long long)P.pitch + ys];
+        if (P.gy && (ys == 0 || ys == P.NY - 1)) return P.snap_col[((ys ? 1 : 0) * 9 + i) * (long long)P.NX + xs];
+    }
+    return ldS(P.src + i * P.plane + (long long)xs * P.pitch + ys);
+}
+
+// Values of time t are reconstructed from S_{t-1}, ghost cells included. A neighbour that is one step ahead
+// overwrites MY ghost cells of that buffer with its S_{t+1} as soon as I have finished step t — possibly before I
+// materialise time t. So the step kernel keeps a private copy of the ghost ring of the buffer it reads (edge
+// threads copy the ghost cells next to them; ~2(NX+NY) cells), and materialisation reads ghosts from that copy.
+__device__ __forceinline__ void snapshot_ghosts(const StepParams &P, int x, int y)
+{
+    const bool xl = P.gx && x == P.gx, xh = P.gx && x == P.NX - 1 - P.gx;
+    const bool yl = P.gy && y == P.gy, yh = P.gy && y == P.NY - 1 - P.gy;
+    if (!(xl | xh | yl | yh)) return;
+#pragma unroll 1
+    for (int side = 0; side < 2; side++) {
+        if (side ? xh : xl) {
+            const int gx_row = side ? P.NX - 1 : 0;
+            const double *src = P.src + (long long)gx_row * P.pitch;
+            double *dst = P.snap_row + (long long)side * 9 * P.pitch;
+            for (int i = 0; i < 9; i++) {
+                dst[i * (long long)P.pitch + y] = ldS(src + i * P.plane + y);
+                if (yl) dst[i * (long long)P.pitch] = ldS(src + i * P.plane);
+                if (yh) dst[i * (long long)P.pitch + P.NY - 1] = ldS(src + i * P.plane + P.NY - 1);
+            }
+        }
+        if (side ? yh : yl) {
+            const int gy_col = side ? P.NY - 1 : 0;
+            double *dst = P.snap_col + (long long)side * 9 * P.NX;
+            for (int i = 0; i < 9; i++) dst[i * (long long)P.NX + x] = ldS(P.src + i * P.plane + (long long)x * P.pitch + gy_col);
+        }
+    }
+}
 
 // f_post of one fluid cell: nine pulls with periodic wrap over the local array (np.roll semantics)
 __device__ __forceinline__ void pull_fluid(const StepParams &P, int x, int y, double (&f)[9])
@@ -139,7 +183,7 @@ __device__ __forceinline__ double pull_rule(const StepParams &P, const lbm_kind 
         int xs = x - cx[I], ys = y - cy[I];
         xs = xs < 0 ? P.NX - 1 : (xs >= P.NX ? 0 : xs);
         ys = ys < 0 ? P.NY - 1 : (ys >= P.NY ? 0 : ys);
-        return ldS(P.src + I * pl + (long long)xs * P.pitch + ys);
+        return ld_cell(P, I, xs, ys);
     }
     if (type == LBM_RULE_BOUNCE) {
         const double v = ldS(P.src + opp[I] * pl + (long long)x * P.pitch + y);
@@ -239,7 +283,7 @@ __device__ __forceinline__ void halo_wait(const StepParams &P)
         for (int s = 0; s < 9; s++) {
             if (!P.flag_out[s]) continue;   // not a remote neighbour
             while ((int)(P.flag_in[s] - P.wait_value) < 0) {
-                if (clock64() - t0 > 20000000000LL) {   // ~10 s: a peer is not stepping in lockstep
+                if (clock64() - t0 > P.timeout_cycles) {   // a peer is not stepping in lockstep
                     atomicExch(P.err_flag, 1u);
                     break;
                 }
@@ -311,7 +355,10 @@ __device__ __forceinline__ void finish_cell(const StepParams &P, int x, int y, c
     }
     store_cell(P, x, y, s, skip);
     if (flags & (LBM_CELL_PBC_IN_SRC | LBM_CELL_PBC_OUT_SRC)) store_pbc(P, flags, y, s, p, e);
-    if (HALO) store_halo(P, x, y, s);
+    if (HALO) {
+        store_halo(P, x, y, s);
+        snapshot_ghosts(P, x, y);
+    }
 }
 
 // A non-fluid cell. Everything is inlined with compile-time population indices: the first version called an
@@ -351,7 +398,18 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepParams
             rule_cell<HALO, FINAL>(P, x, y, kind);
         } else {
             double f[9];
-            pull_fluid(P, x, y, f);
+            if (FINAL && P.use_snap) {
+                constexpr int cx[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1}, cy[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
+#pragma unroll
+                for (int i = 0; i < 9; i++) {
+                    int xs = x - cx[i], ys = y - cy[i];
+                    xs = xs < 0 ? P.NX - 1 : (xs >= P.NX ? 0 : xs);
+                    ys = ys < 0 ? P.NY - 1 : (ys >= P.NY ? 0 : ys);
+                    f[i] = ld_cell(P, i, xs, ys);
+                }
+            } else {
+                pull_fluid(P, x, y, f);
+            }
             finish_cell<HALO, FINAL>(P, x, y, f, 0u, 0u);
         }
     }
@@ -587,12 +645,14 @@ struct lbm_ctx {
     lbm_kind *kinds = nullptr;
     double *ktab = nullptr, *ctab = nullptr;
     double *outbuf[2] = {nullptr, nullptr};
+    double *snap_row = nullptr, *snap_col = nullptr;
     int2 *cells = nullptr;
     int n_cells = 0;
     bool has_bc = false;
     double rho_in = 0, rho_out = 0;
     int bc_mode = LBM_BC_AUTO;
     unsigned *done_counter = nullptr, *err_flag = nullptr;
+    long long timeout_cycles = 30LL * 2000000000LL;   // ~30 s at 2 GHz; LBM_HALO_TIMEOUT_S overrides
     // staging for upload / materialize (reference layout, a chunk of rows)
     double *stage_f = nullptr, *stage_rho = nullptr, *stage_u = nullptr;
     long long stage_cells = 0;
@@ -793,7 +853,7 @@ extern "C" int lbm_destroy(lbm_ctx *c)
             for (int q = 0; q < s; q++) shared |= c->peer[q].mapped == c->peer[s].mapped;
             if (!shared) cudaIpcCloseMemHandle(c->peer[s].mapped);
         }
-    void *bufs[] = {c->arena,  c->kind_map, c->kinds,    c->ktab,   c->ctab,  c->outbuf[0],   c->outbuf[1], c->cells,
+    void *bufs[] = {c->arena,  c->kind_map, c->kinds,    c->ktab,   c->ctab,  c->outbuf[0],   c->outbuf[1], c->cells, c->snap_row, c->snap_col,
                     c->done_counter, c->err_flag, c->stage_f, c->stage_rho, c->stage_u, c->mm_acc, c->probe};
     for (void *b : bufs)
         if (b) cudaFree(b);
@@ -840,6 +900,13 @@ static int ctx_build(lbm_ctx *c, const lbm_bc_desc *bc)
     for (int b = 0; b < 2; b++) {
         CK(cudaMalloc(&c->outbuf[b], (size_t)3 * c->pitch * 8));
         CK(cudaMemset(c->outbuf[b], 0, (size_t)3 * c->pitch * 8));
+    }
+
+    if (c->gx || c->gy) {
+        CK(cudaMalloc(&c->snap_row, (size_t)2 * 9 * c->pitch * 8));
+        CK(cudaMemset(c->snap_row, 0, (size_t)2 * 9 * c->pitch * 8));
+        CK(cudaMalloc(&c->snap_col, (size_t)2 * 9 * c->NX * 8));
+        CK(cudaMemset(c->snap_col, 0, (size_t)2 * 9 * c->NX * 8));
     }
 
     // staging: a chunk of rows in reference layout (96 B per cell), at most ~256 MB
@@ -910,6 +977,7 @@ extern "C" int lbm_create(int device, int nx, int ny, int ghost_x, int ghost_y, 
     c->gy = ghost_y;
     c->pitch = (ny + 15) & ~15;
     c->plane = (long long)nx * c->pitch;
+    if (const char *t = getenv("LBM_HALO_TIMEOUT_S")) c->timeout_cycles = (long long)(atof(t) * 2e9);
     if (int rc = ctx_build(c, bc)) {
         std::string keep = g_err;
         lbm_destroy(c);
@@ -963,9 +1031,12 @@ static void fill_common(const lbm_ctx *c, StepParams &P, int src_buf, int dst_bu
     P.rho_out = c->rho_out;
     P.px = -1;
     P.py = -1;
+    P.snap_row = c->snap_row;
+    P.snap_col = c->snap_col;
     P.cells = c->cells;
     P.n_cells = c->n_cells;
     P.done_counter = c->done_counter;
+    P.timeout_cycles = c->timeout_cycles;
     P.err_flag = c->err_flag;
     P.flag_in = c->flags_in;
 }
@@ -1221,6 +1292,7 @@ static int materialize_rows(lbm_ctx *c, int x0, int x1, int y0, int y1, double *
 {
     StepParams P;
     fill_common(c, P, c->cur ^ 1, c->cur, c->omega);
+    P.use_snap = c->halo_ready && c->snap_row ? 1 : 0;
     const int w = y1 - y0;
     const long long chunk_rows = std::max<long long>(1, c->stage_cells / w);
     for (int xa = x0; xa < x1; xa += (int)chunk_rows) {

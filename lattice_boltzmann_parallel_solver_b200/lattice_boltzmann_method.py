@@ -5,6 +5,7 @@ assertion behaviour; every array operation runs on the GPU through the C-ABI of 
 per call) but its results are lazy, device-resident `LatticeArray` handles (engine.py); passing them back in
 — the loop every driver of the reference runs — advances the resident lattice by one fused kernel launch.
 """
+import atexit
 from typing import Callable, Tuple
 
 import numpy as np
@@ -125,6 +126,21 @@ def release_lattices():
         _lattices.popitem()[1][0].close()
 
 
+def _flush_at_exit():
+    # A rank whose loop ended with a deferred step must still launch it: neighbouring ranks' kernels of the same
+    # step wait for its "begun" flag (include/lbm_b200.h, halo section).
+    for lat, _, comm in list(_lattices.values()):
+        if comm is not None and lat._pending is not None:
+            try:
+                lat.flush()
+                lat.sync()
+            except Exception:
+                pass
+
+
+atexit.register(_flush_at_exit)
+
+
 def lattice_boltzmann_step(f: np.ndarray, density: np.ndarray, velocity: np.ndarray, omega: float,
                            boundary: Callable = None,
                            parallel_communication: Callable = None) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
@@ -138,6 +154,8 @@ def lattice_boltzmann_step(f: np.ndarray, density: np.ndarray, velocity: np.ndar
     lat = _lattice_for(shape, boundary, parallel_communication)
     if not lat.is_current(f, density, velocity):
         lat.reset_for_upload()
+        if parallel_communication is not None:
+            parallel_communication.before_load(lat)
         lat.load(np.asarray(f), np.asarray(density), np.asarray(velocity), omega)
         if parallel_communication is not None:
             parallel_communication.after_load(lat)

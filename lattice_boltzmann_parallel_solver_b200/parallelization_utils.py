@@ -63,6 +63,11 @@ class HaloExchange:
         lattice.halo_finalize()
         self._barrier()
 
+    def before_load(self, lattice):
+        """A fresh upload stores ghost cells into the neighbours' buffers: every rank must be done reading the
+        previous run's state first."""
+        self._barrier()
+
     def after_load(self, lattice):
         """Every rank's first-collision ghost stores must have landed before anyone takes the first step."""
         self._barrier()
