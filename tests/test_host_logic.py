@@ -204,3 +204,61 @@ def test_cart_comm_matches_mpi_cart_semantics():
     assert np.array_equal(PU.communication(cart)(f.copy()), onp.self_exchange(f.copy()))
     with pytest.raises(AssertionError):
         w.Create_cart(dims=[2, 1])
+
+
+def test_dropin_modules_expose_the_reference_api():
+    """Flat imports from the dropin directory (how the reference's drivers import, Makefile:3) expose every public
+    function of the reference modules with the same parameter names. Names are pinned here; when the reference
+    tree is present (build container) the list is re-derived from it."""
+    import importlib
+    import inspect
+    dropin = os.path.join(ROOT, 'lattice_boltzmann_parallel_solver_b200', 'dropin')
+    sys.path.insert(0, dropin)
+    try:
+        expected = {
+            'lattice_boltzmann_method': {
+                'get_velocity_sets': [], 'vel_to_opp_vel_mapping': [], 'get_w_i': [], 'reynolds_number': ['L', 'u', 'v'],
+                'strouhal_number': ['f', 'L', 'u'], 'compute_density': ['prob_densitiy_func'],
+                'compute_velocity_field': ['density_func', 'prob_density_func'], 'streaming': ['prob_density_func'],
+                'equilibrium_distr_func': ['density_func', 'velocity_field'],
+                'lattice_boltzmann_step': ['f', 'density', 'velocity', 'omega', 'boundary', 'parallel_communication']},
+            'boundary_conditions': {
+                'get_wall_indices': ['boundary'], 'get_corner_indices': ['boundary'],
+                'remove_corner_indices_from_boundary': ['boundary', 'corner_indices'], 'rigid_wall': ['boundary'],
+                'rigid_object': ['boundary'], 'moving_wall': ['boundary', 'u_w', 'avg_density'],
+                'inlet': ['lattice_grid_shape', 'density_in', 'velocity_in'], 'outlet': [],
+                'periodic_with_pressure_variations': ['boundary', 'p_in', 'p_out']},
+            'boundary_utils': {
+                'couette_flow_boundary_conditions': ['lx', 'ly', 'U', 'avg_density'],
+                'poiseuille_flow_boundary_conditions': ['lx', 'ly', 'p_in', 'p_out'],
+                'parallel_von_karman_boundary_conditions': ['coord2d', 'n_local_x', 'n_local_y', 'lx', 'ly', 'x_size',
+                                                            'y_size', 'density_in', 'velocity_in', 'plate_size']},
+            'parallelization_utils': {
+                'communication': ['comm'], 'get_xy_size': ['total_number_of_procces'],
+                'get_local_coords': ['coords2d', 'lx', 'ly', 'x_size', 'y_size'],
+                'global_to_local_direction': ['coord1d', 'global_dir', 'lattice_dir', 'dir_size'],
+                'global_coord_to_local_coord': ['coord2d', 'global_x', 'global_y', 'lx', 'ly', 'x_size', 'y_size'],
+                'x_in_process': ['coord2d', 'x_coord', 'lx', 'processes_in_x'],
+                'y_in_process': ['coord2d', 'y_coord', 'ly', 'processes_in_y'], 'save_mpiio': ['comm', 'fn', 'g_kl']},
+        }
+        ref_src = '/root/reference/src'
+        if os.path.isdir(ref_src):
+            import ast
+            for mod, table in expected.items():
+                tree = ast.parse(open(os.path.join(ref_src, mod + '.py')).read())
+                found = {n.name: [a.arg for a in n.args.args] for n in tree.body if isinstance(n, ast.FunctionDef)}
+                assert found == table, mod
+        for mod, table in expected.items():
+            for cached in [m for m in sys.modules if m == mod]:
+                del sys.modules[cached]
+            m = importlib.import_module(mod)
+            assert m.__file__.startswith(dropin)
+            for name, params in table.items():
+                fn = getattr(m, name)
+                assert list(inspect.signature(fn).parameters) == params, (mod, name)
+        from mpi4py import MPI
+        assert MPI.COMM_WORLD.Get_size() == 1 and hasattr(MPI, 'Intracomm')
+    finally:
+        sys.path.remove(dropin)
+        for mod in list(expected) + ['mpi4py', 'mpi4py.MPI']:
+            sys.modules.pop(mod, None)
