@@ -305,6 +305,15 @@ def run_e2e(args, lat, world, rank, nx_local, ny, prof, barrier):
     g = lat.ghost[0]
     NX = nx_local + 2 * g
     cells = NX * ny
+    need = cells * 96 * max(1, int(os.environ.get('LOCAL_WORLD_SIZE', world)))
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = None
+    if avail is not None and need > 0.5 * avail:
+        return {'value': None, 'unit': 'MLUPS', 'h2d_bytes_per_step': None, 'd2h_bytes_per_step': None,
+                'skipped': f'pinned host staging of {need / 1e9:.0f} GB exceeds half of the available host memory ({avail / 1e9:.0f} GB)'}
     try:
         hf = torch.empty((NX, ny, 9), dtype=torch.float64, pin_memory=True).numpy()
         hr = torch.empty((NX, ny), dtype=torch.float64, pin_memory=True).numpy()
