@@ -417,6 +417,81 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepParams
 }
 
 // -------------------------------------------------------------------------------------------------------
+// The bandwidth kernel: fluid cells only (no kind byte, no ghost stores), TWO cells per thread along the fast axis.
+//  * blockIdx.y is the row (no integer division), the three row bases are computed once per thread;
+//  * the three populations that do not move along y (0, 1, 3) are read with 128-bit loads, the six shifted ones
+//    with two 64-bit loads off one address register (+-1 element: 8 B alignment only);
+//  * all nine populations of both cells are written with 128-bit stores.
+// Same per-cell arithmetic as k_step (lbm_device.cuh), hence the same bits.
+// -------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 ld2(const double *p)
+{
+    double2 v;
+    asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st2(double *p, double a, double b)
+{
+    asm volatile("st.global.cg.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+}
+
+__global__ void __launch_bounds__(256) k_step_pair(const __grid_constant__ StepParams P)
+{
+    const int x = P.row0a + blockIdx.y;
+    const int y = 2 * (blockIdx.x * blockDim.x + threadIdx.x);   // cells y, y+1; NY is even
+    if (y >= P.NY) return;
+    const int xm = x == 0 ? P.NX - 1 : x - 1, xp = x == P.NX - 1 ? 0 : x + 1;
+    const int ym = y == 0 ? P.NY - 1 : y - 1;          // left neighbour of the first cell
+    const int yq = y + 2 == P.NY ? 0 : y + 2;          // right neighbour of the second cell
+    const long long pl = P.plane;
+    const double *r0 = P.src + (long long)x * P.pitch;
+    const double *rm = P.src + (long long)xm * P.pitch;
+    const double *rp = P.src + (long long)xp * P.pitch;
+
+    double fa[9], fb[9];
+    {
+        const double2 v0 = ld2(r0 + y), v1 = ld2(rm + pl + y), v3 = ld2(rp + 3 * pl + y);
+        fa[0] = v0.x; fb[0] = v0.y;
+        fa[1] = v1.x; fb[1] = v1.y;
+        fa[3] = v3.x; fb[3] = v3.y;
+        // c_y = +1: cell y pulls from y-1, cell y+1 pulls from y
+        fa[2] = ldS(r0 + 2 * pl + ym); fb[2] = ldS(r0 + 2 * pl + y);
+        fa[5] = ldS(rm + 5 * pl + ym); fb[5] = ldS(rm + 5 * pl + y);
+        fa[6] = ldS(rp + 6 * pl + ym); fb[6] = ldS(rp + 6 * pl + y);
+        // c_y = -1: cell y pulls from y+1, cell y+1 pulls from y+2
+        fa[4] = ldS(r0 + 4 * pl + y + 1); fb[4] = ldS(r0 + 4 * pl + yq);
+        fa[7] = ldS(rp + 7 * pl + y + 1); fb[7] = ldS(rp + 7 * pl + yq);
+        fa[8] = ldS(rm + 8 * pl + y + 1); fb[8] = ldS(rm + 8 * pl + yq);
+    }
+    double sa[9], sb[9];
+    {
+        double rho, ux, uy, p[9], e[9];
+        moments(fa, rho, ux, uy);
+        if (P.probe_slot && x == P.px && y == P.py) {
+            P.probe_slot[0] = ux;
+            P.probe_slot[1] = uy;
+        }
+        eq_poly(ux, uy, p);
+        eq_from_poly(rho, p, e);
+        collide(fa, e, P.omega, sa);
+    }
+    {
+        double rho, ux, uy, p[9], e[9];
+        moments(fb, rho, ux, uy);
+        if (P.probe_slot && x == P.px && y + 1 == P.py) {
+            P.probe_slot[0] = ux;
+            P.probe_slot[1] = uy;
+        }
+        eq_poly(ux, uy, p);
+        eq_from_poly(rho, p, e);
+        collide(fb, e, P.omega, sb);
+    }
+    double *d = P.dst + (long long)x * P.pitch + y;
+#pragma unroll
+    for (int i = 0; i < 9; i++) st2(d + i * pl, sa[i], sb[i]);
+}
+
+// -------------------------------------------------------------------------------------------------------
 // first collision of an uploaded / initialised state: S_0 = f + (feq(rho,u) - f)*omega with the GIVEN moments
 // (lattice_boltzmann_method.py:213-215). Input is either reference-layout staging (rows [x0, x0+nrows)) or the
 // separable initial fields of initial_values.py.
@@ -506,8 +581,8 @@ __global__ void k_moments(long long n, const double *f, const double *rho_in, do
             const double r = rho_in[c];
             const double jx = sub(add(add(g[1], g[5]), g[8]), add(add(g[3], g[6]), g[7]));
             const double jy = sub(add(add(g[2], g[5]), g[6]), add(add(g[4], g[7]), g[8]));
-            ux = r != 0.0 ? __ddiv_rn(jx, r) : 0.0;
-            uy = r != 0.0 ? __ddiv_rn(jy, r) : 0.0;
+            ux = r != 0.0 ? div_rn(jx, r) : 0.0;
+            uy = r != 0.0 ? div_rn(jy, r) : 0.0;
         }
         u_out[2 * c] = ux;
         u_out[2 * c + 1] = uy;
@@ -651,6 +726,7 @@ struct lbm_ctx {
     bool has_bc = false;
     double rho_in = 0, rho_out = 0;
     int bc_mode = LBM_BC_AUTO;
+    bool force_generic = false;   // LBM_GENERIC_KERNEL=1: always use the one-cell-per-thread kernel (A/B measurements)
     unsigned *done_counter = nullptr, *err_flag = nullptr;
     long long timeout_cycles = 30LL * 2000000000LL;   // ~30 s at 2 GHz; LBM_HALO_TIMEOUT_S overrides
     // staging for upload / materialize (reference layout, a chunk of rows)
@@ -977,6 +1053,7 @@ extern "C" int lbm_create(int device, int nx, int ny, int ghost_x, int ghost_y, 
     c->gy = ghost_y;
     c->pitch = (ny + 15) & ~15;
     c->plane = (long long)nx * c->pitch;
+    if (const char *g = getenv("LBM_GENERIC_KERNEL")) c->force_generic = atoi(g) != 0;
     if (const char *t = getenv("LBM_HALO_TIMEOUT_S")) c->timeout_cycles = (long long)(atof(t) * 2e9);
     if (int rc = ctx_build(c, bc)) {
         std::string keep = g_err;
@@ -1094,7 +1171,13 @@ static int rows_launch(lbm_ctx *c, StepParams P, int row0a, int na, int row0b, i
     const int blocks = (na + nb) * P.bpr;
     P.n_blocks = blocks;
     cudaError_t e;
-    if (mask)
+    if (!mask && !halo && nb == 0 && !c->gy && (c->NY % 2) == 0 && c->NY >= 64 && na <= 65535 && !c->force_generic) {
+        // bandwidth kernel: two cells per thread, 2-D grid
+        const int pairs = c->NY / 2, pbs = pairs >= 128 ? 128 : std::max(32, (pairs + 31) & ~31);
+        dim3 grid((pairs + pbs - 1) / pbs, na);
+        k_step_pair<<<grid, pbs, 0, st>>>(P);
+        e = cudaGetLastError();
+    } else if (mask)
         e = halo ? launch<true, true, false, false>(P, blocks, bs, st) : launch<true, false, false, false>(P, blocks, bs, st);
     else
         e = halo ? launch<false, true, false, false>(P, blocks, bs, st) : launch<false, false, false, false>(P, blocks, bs, st);

@@ -29,6 +29,9 @@ Fixtures written (all float64, bit patterns of the reference's numpy results):
   ref_probe_100.npy  first 2001 samples of the cluster-generated trace
                      figures/von_karman_vortex_shedding/reynold_strouhal/vel_at_p_100.npy
   ref_vel_at_p.npy   tests/von_karman_vortex_shedding/vel_at_p.npy (12 samples)
+  observables.npz    published fit numbers (figures/couette_flow/linregress.csv, figures/poiseuille_flow/*.csv),
+                     the reference re-run on the published Poiseuille config (40 000 steps), viscosity fits
+  ref_probe_100_full.npy  the whole 200 001-sample cluster trace at Re = 100 (Strouhal check)
 """
 import hashlib
 import json
@@ -455,6 +458,71 @@ def gen_karman_ranks(f11_serial):
     np.savez_compressed(os.path.join(OUT, 'karman_ranks.npz'), **out)
 
 
+def gen_observables():
+    """Long-run observables the north star bounds to 0.5 %: published numbers (figures/*.csv), the reference run
+    again here on the published configs, the viscosity fit of experiments.py:147-223 on a few omegas, and the full
+    200 001-sample cluster trace at Re=100 (figures/von_karman_vortex_shedding/reynold_strouhal/vel_at_p_100.npy)."""
+    import csv
+    from scipy.optimize import curve_fit
+    from scipy.signal import argrelextrema
+    out = {}
+    with open(os.path.join(REF, 'figures/couette_flow/linregress.csv')) as fh:
+        row = list(csv.DictReader(fh))[0]
+    out['couette_published'] = np.array([float(row['slope']), float(row['intercept']), float(row['rvalue'])])
+    with open(os.path.join(REF, 'figures/poiseuille_flow/areas.csv')) as fh:
+        row = list(csv.DictReader(fh))[0]
+    out['poiseuille_areas_published'] = np.array([float(row['inlet']), float(row['middle']), float(row['relative_difference'])])
+    out['poiseuille_fit_published'] = np.array([-4.47780943e-05, 2.64190756e-03, 1.33776993e-03])  # curve_fit.csv popt
+    # Poiseuille at the published config (experiments.py:377-406): 200x60, omega 1.5, dp 0.001, 40 000 steps
+    lx, ly, om, dp = 200, 60, 1.5, 0.001
+    rho_in, rho_out = 1 + (dp * 3) / 2, 1 - (dp * 3) / 2
+    p_in, p_out = rho_in / 3, rho_out / 3
+    bc = BU.poiseuille_flow_boundary_conditions(lx, ly, p_in, p_out)
+    rho, u = I.density_1_velocity_0_initial((lx, ly))
+    f = L.equilibrium_distr_func(rho, u)
+    for t in range(40000):
+        f, rho, u = L.lattice_boltzmann_step(f, rho, u, om, bc)
+    out['poiseuille_p'] = np.array([p_in, p_out])
+    out['poiseuille_ux_x1'] = u[1, :, 0].copy()
+    out['poiseuille_ux_mid'] = u[lx // 2, :, 0].copy()
+    out['poiseuille_rho_centerline'] = rho[:, ly // 2].copy()
+    digests('poiseuille_t40000', f, rho, u, out)
+    # viscosity vs omega (experiments.py:147-223), 50x50, 2500 steps, a subset of the 50 omegas
+    shape, steps = (50, 50), 2500
+    omegas = np.linspace(0.01, 1.99, 50)[[2, 12, 24, 37, 47]]
+    out['visc_omegas'] = omegas
+    sims = [[], []]
+    for i, initial in enumerate([I.sinusoidal_density_x(shape, 0.5, 0.08), I.sinusoidal_velocity_x(shape, 0.08)]):
+        for k, omg in enumerate(omegas):
+            rho, u = initial
+            f = L.equilibrium_distr_func(rho, u)
+            amp = []
+            for _ in range(steps):
+                f, rho, u = L.lattice_boltzmann_step(f, rho, u, omg)
+                if i == 0:
+                    lo, hi = np.amin(rho), np.amax(rho)
+                    amp.append(np.abs(lo) - 0.5 if np.abs(lo) > np.abs(hi) else np.abs(hi) - 0.5)
+                else:
+                    lo, hi = np.amin(u), np.amax(u)
+                    amp.append(np.abs(lo) if np.abs(lo) > np.abs(hi) else np.abs(hi))
+            amp = np.array(amp)
+            out[f'visc_amp_{i}_{k}'] = amp
+            if i == 0:
+                idx = argrelextrema(amp, np.greater)
+                v = curve_fit(lambda t, v: 0.08 * np.exp(-v * np.power(2 * np.pi / shape[0], 2) * t),
+                              np.array(idx).squeeze(), amp[idx])[0][0]
+            else:
+                v = curve_fit(lambda t, v: 0.08 * np.exp(-v * np.power(2 * np.pi / shape[-1], 2) * t),
+                              np.arange(0, steps), amp)[0][0]
+            sims[i].append(v)
+    out['visc_sim_density'] = np.array(sims[0])
+    out['visc_sim_velocity'] = np.array(sims[1])
+    out['visc_true'] = (1 / 3) * (1 / omegas - 0.5)
+    np.savez_compressed(os.path.join(OUT, 'observables.npz'), **out)
+    trace = np.load(os.path.join(REF, 'figures/von_karman_vortex_shedding/reynold_strouhal/vel_at_p_100.npy'))
+    np.save(os.path.join(OUT, 'ref_probe_100_full.npy'), trace)
+
+
 if __name__ == '__main__':
     which = sys.argv[1:] or ['kernels', 'bc', 'topology', 'shear', 'couette', 'poiseuille', 'karman']
     if 'kernels' in which:
@@ -469,6 +537,8 @@ if __name__ == '__main__':
         gen_couette()
     if 'poiseuille' in which:
         gen_poiseuille()
+    if 'observables' in which:
+        gen_observables()
     if 'karman' in which:
         f11 = gen_karman()
         gen_karman_serial(f11)
