@@ -98,6 +98,82 @@ def cpu_reference_mlups(n, steps, warmup):
     return n * n * steps / dt / 1e6, dt
 
 
+def _cpu_worker(rank, k, n, steps, warmup, shm_name, barrier, out, check_name=None):
+    """One rank of the reference's parallel path (experiments.py:723-767 shape: collide, halo exchange, stream,
+    moments) on a slab of the n x n periodic shear-wave lattice; the four Sendrecv of parallelization_utils.py:34-49
+    go through a shared-memory mailbox (there is no MPI in the image)."""
+    from multiprocessing import shared_memory
+    from oracle import lbm_numpy as onp
+    os.environ['OMP_NUM_THREADS'] = '1'
+    nloc = n // k
+    shm = shared_memory.SharedMemory(name=shm_name)
+    mail = np.ndarray((k, 2, n + 2, 9), dtype=np.float64, buffer=shm.buf)
+    rho, u = onp.sinusoidal_velocity_x((nloc + 2, n + 2), EPS)
+    prof = EPS * np.sin(np.divide(2 * np.pi * ((np.arange(n + 2) - 1) % n), n))
+    u[..., 0] = prof[None, :]
+    f = onp.equilibrium(rho, u)
+    left, right = (rank - 1) % k, (rank + 1) % k
+
+    def comm(fp):
+        mail[rank, 0] = fp[1]          # my first interior row  -> left neighbour's high ghost row
+        mail[rank, 1] = fp[-2]         # my last interior row   -> right neighbour's low ghost row
+        barrier.wait()
+        fp[-1] = mail[right, 0]
+        fp[0] = mail[left, 1]
+        barrier.wait()
+        fp[:, -1, :] = fp[:, 1, :]     # one rank along y: self copies, after the x faces (carry the corners)
+        fp[:, 0, :] = fp[:, -2, :]
+        return fp
+
+    for _ in range(warmup):
+        f, rho, u = onp.step(f, rho, u, OMEGA, None, comm)
+    barrier.wait()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        f, rho, u = onp.step(f, rho, u, OMEGA, None, comm)
+    barrier.wait()
+    out[rank] = time.perf_counter() - t0
+    if check_name:   # tests: gather the interiors so the decomposition can be compared with one process
+        chk = shared_memory.SharedMemory(name=check_name)
+        np.ndarray((n, n, 9), dtype=np.float64, buffer=chk.buf)[rank * nloc:(rank + 1) * nloc] = f[1:-1, 1:-1]
+        chk.close()
+    shm.close()
+
+
+def cpu_reference_mlups_parallel(n, steps, warmup, k, return_fields=False):
+    """k processes (one per host core), slabs along x with a ghost ring — how the reference uses more than one core
+    (mpirun -N k, README.md:47-48)."""
+    import multiprocessing as mp
+    from multiprocessing import shared_memory
+    ctx = mp.get_context('fork')
+    shm = shared_memory.SharedMemory(create=True, size=k * 2 * (n + 2) * 9 * 8)
+    barrier = ctx.Barrier(k)
+    out = ctx.Array('d', k)
+    chk = shared_memory.SharedMemory(create=True, size=n * n * 72) if return_fields else None
+    procs = [ctx.Process(target=_cpu_worker, args=(r, k, n, steps, warmup, shm.name, barrier, out,
+                                                   chk.name if chk else None)) for r in range(k)]
+    [p.start() for p in procs]
+    [p.join() for p in procs]
+    shm.close()
+    shm.unlink()
+    fields = None
+    if chk:
+        fields = np.ndarray((n, n, 9), dtype=np.float64, buffer=chk.buf).copy()
+        chk.close()
+        chk.unlink()
+    if any(p.exitcode != 0 for p in procs):
+        raise RuntimeError('CPU baseline worker failed')
+    dt = max(out[:])
+    return (n * n * steps / dt / 1e6, dt, fields) if return_fields else (n * n * steps / dt / 1e6, dt)
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def cpu_model():
     try:
         with open('/proc/cpuinfo') as fh:
@@ -110,21 +186,37 @@ def cpu_model():
 
 
 def run_reference(args, rank):
-    """--impl reference: the reference's CPU algorithm (oracle port, kind "port") on the host cores; each step a
-    bounded sample of the workload (one time step on an n x n lattice, n = 2048)."""
+    """--impl reference: the reference's CPU algorithm (oracle port of its numpy path, kind "port") on ALL host
+    cores: k = largest power of two <= cores processes, slab decomposition + ghost exchange as under mpirun -N k.
+    Each step is a bounded sample of the workload: one time step of an n x n lattice (n = --cpu-size)."""
     if rank != 0:
         return
     n = args.cpu_size
-    mlups, dt = cpu_reference_mlups(n, args.steps, args.warmup)
+    k = 1
+    while k * 2 <= host_cores() and n % (k * 2) == 0 and k * 2 <= 64:
+        k *= 2
+    if args.cpu_procs:
+        k = args.cpu_procs
+    # bound the sample: the whole --steps/--warmup run must end within a few minutes on this host
+    while n > 256:
+        probe = cpu_reference_mlups_parallel(n, 1, 1, k)[1] if k > 1 else cpu_reference_mlups(n, 1, 1)[1]
+        if probe * (args.steps + args.warmup) <= 150.0:
+            break
+        n //= 2
+    if k > 1:
+        mlups, dt = cpu_reference_mlups_parallel(n, args.steps, args.warmup, k)
+    else:
+        mlups, dt = cpu_reference_mlups(n, args.steps, args.warmup)
     sample = (f'{n}x{n} periodic shear wave (same fields/omega as the GPU arm, which runs {args.size}^2 per GPU; the '
-              f'numpy path needs ~400 B/cell so the full size does not fit/finish), {args.steps} steps, 1 process: numpy '
-              f'ufuncs are single-threaded; host has {os.cpu_count()} logical cores, {cpu_model()}')
+              f'numpy path needs ~400 B/cell so the full size does not fit/finish), {args.steps} steps after '
+              f'{args.warmup} warm-up, {k} processes x 1 thread (numpy ufuncs are single-threaded; slabs + ghost-row '
+              f'exchange through shared memory, as mpirun -N {k}); host: {host_cores()} usable cores, {cpu_model()}')
     line = {
         'impl': 'reference', 'metric': 'D2Q9 fp64 MLUPS', 'value': mlups, 'unit': 'MLUPS', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': workload_config(args, 1),
-        'cpu_baseline': {'value': mlups, 'unit': 'MLUPS', 'cores': 1, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': {'value': mlups, 'unit': 'MLUPS', 'cores': k, 'kind': 'port', 'sample': sample},
         'e2e': {'value': mlups, 'unit': 'MLUPS', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line), flush=True)
@@ -152,6 +244,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--cpu-size', type=int, default=2048)
     ap.add_argument('--cpu-steps', type=int, default=4)
+    ap.add_argument('--cpu-procs', type=int, default=0, help='processes of the CPU reference arm (default: all cores)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--e2e-size', type=int, default=0, help='lattice edge of the e2e job (default: --size)')
@@ -239,7 +332,7 @@ def main():
     achieved = per_gpu_cells * ALGO_BYTES_PER_UPDATE / (ms * 1e-3 / args.steps) / 1e9
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                 'traffic': None, 'peak_source': peak_src,
-                'kernel': 'k_step<MASK=0,HALO=0,FINAL=0,LIST=0>',
+                'kernel': 'k_step_pair (interior rows; two cells per thread)',
                 'algorithmic_bytes_per_launch': per_gpu_cells * ALGO_BYTES_PER_UPDATE,
                 'mlups_at_peak': peak * 1e9 / ALGO_BYTES_PER_UPDATE / 1e6,
                 'frac_of_nominal_8TBps': achieved / 8000.0}
@@ -259,11 +352,19 @@ def main():
 
     cpu = None
     if rank == 0 and not args.no_cpu:
-        v, dt = cpu_reference_mlups(args.cpu_size, args.cpu_steps, 1)
-        cpu = {'value': v, 'unit': 'MLUPS', 'cores': 1, 'kind': 'port',
-               'sample': f'{args.cpu_size}x{args.cpu_size} periodic shear wave, {args.cpu_steps} steps after 1 warm-up, '
-                         f'oracle/lbm_numpy.py (numpy restatement of the reference, single-threaded ufuncs); host: '
-                         f'{os.cpu_count()} logical cores, {cpu_model()}; {dt:.1f} s'}
+        k = 1
+        while k * 2 <= host_cores() and args.cpu_size % (k * 2) == 0 and k * 2 <= 64:
+            k *= 2
+        k = args.cpu_procs or k
+        steps_cpu = args.cpu_steps * (4 if k > 1 else 1)
+        v, dt = (cpu_reference_mlups_parallel(args.cpu_size, steps_cpu, 1, k) if k > 1 else
+                 cpu_reference_mlups(args.cpu_size, steps_cpu, 1))
+        v1, dt1 = cpu_reference_mlups(args.cpu_size, 2, 1)
+        cpu = {'value': v, 'unit': 'MLUPS', 'cores': k, 'kind': 'port', 'single_core_value': v1,
+               'sample': f'{args.cpu_size}x{args.cpu_size} periodic shear wave, {steps_cpu} steps after 1 warm-up, '
+                         f'oracle/lbm_numpy.py (numpy restatement of the reference) on {k} processes x 1 thread with '
+                         f'slab decomposition + ghost-row exchange (as mpirun -N {k}); host: {host_cores()} usable '
+                         f'cores, {cpu_model()}; {dt:.1f} s; one process alone: {v1:.2f} MLUPS'}
     if rank == 0:
         line = {
             'metric': 'D2Q9 fp64 MLUPS', 'value': mlups, 'unit': 'MLUPS', 'n_gpus': world, 'steps': args.steps,

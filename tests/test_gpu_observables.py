@@ -21,13 +21,9 @@ def P():
 
 
 def strouhal_from_trace(vel_at_p, cut=70000, d=40, u=0.1):
-    """visualizations_utils.py:150-167 (Re = 100 branch)."""
-    v = np.array(vel_at_p[cut:], dtype=np.float64)
-    v -= np.mean(v)
-    yf = np.fft.fft(v)
-    freq = np.fft.fftfreq(len(v), 1)
-    f = np.abs(freq[np.argmax(np.abs(yf))])
-    return np.divide(f * d, u), f
+    """visualizations_utils.py:150-167 (Re = 100 branch), through the package's estimator."""
+    from lattice_boltzmann_parallel_solver_b200 import observables as O
+    return O.strouhal_from_trace(vel_at_p, d, u, cut), O.vortex_frequency(vel_at_p, cut)
 
 
 def test_strouhal_number_200k_steps(P):
@@ -82,15 +78,9 @@ def test_viscosity_vs_omega(P):
                     amp.append(np.abs(lo) if np.abs(lo) > np.abs(hi) else np.abs(hi))
             amp = np.array(amp)
             assert np.array_equal(amp, g[f'visc_amp_{i}_{k}']), (i, k)      # the observable series, bit for bit
-            if i == 0:
-                idx = argrelextrema(amp, np.greater)
-                v = curve_fit(lambda t, v: 0.08 * np.exp(-v * np.power(2 * np.pi / shape[0], 2) * t),
-                              np.array(idx).squeeze(), amp[idx])[0][0]
-                want = g['visc_sim_density'][k]
-            else:
-                v = curve_fit(lambda t, v: 0.08 * np.exp(-v * np.power(2 * np.pi / shape[-1], 2) * t),
-                              np.arange(0, steps), amp)[0][0]
-                want = g['visc_sim_velocity'][k]
+            from lattice_boltzmann_parallel_solver_b200 import observables as O
+            v = O.viscosity_from_decay(amp, 0.08, shape[0] if i == 0 else shape[-1], peaks_only=(i == 0))
+            want = (g['visc_sim_density'] if i == 0 else g['visc_sim_velocity'])[k]
             assert abs(v - want) <= TOL * abs(want)
             if i == 1 and 0.4 <= om <= 1.6:
                 # physics, where the measurement method is valid: nu = (1/omega - 1/2)/3 (experiments.py:210)

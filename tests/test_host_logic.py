@@ -262,3 +262,23 @@ def test_dropin_modules_expose_the_reference_api():
         sys.path.remove(dropin)
         for mod in list(expected) + ['mpi4py', 'mpi4py.MPI']:
             sys.modules.pop(mod, None)
+
+
+def test_cpu_baseline_processes_equal_one_process():
+    """bench.py's all-cores CPU arm (k processes, slabs, shared-memory ghost exchange) computes exactly what the
+    single-process oracle computes."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle import lbm_numpy as onp
+    n, steps = 64, 5
+    _, _, got = bench.cpu_reference_mlups_parallel(n, steps, 0, 4, return_fields=True)
+    rho, u = onp.sinusoidal_velocity_x((n, n), bench.EPS)
+    f = onp.equilibrium(rho, u)
+    for _ in range(steps):
+        f, rho, u = onp.step(f, rho, u, bench.OMEGA)
+    assert np.array_equal(got, f)
+    line = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '2', '--warmup',
+                           '1', '--cpu-size', '256'], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert line.returncode == 0, line.stderr[-2000:]
+    d = json.loads(line.stdout.strip().splitlines()[-1])
+    assert d['impl'] == 'reference' and d['value'] > 0 and d['cpu_baseline']['kind'] == 'port' and d['e2e']['value'] == d['value']
