@@ -84,7 +84,9 @@ struct StepParams {
     double *out_next;          // written by OUTLET_SRC cells
     double rho_in, rho_out;
     int px, py;
-    double *probe_slot;
+    double *probe;             // ring of (ux, uy), probe_cap entries, or null
+    long long *tcount;         // [2]: time of the state in buffer 0 / 1 (device-resident so that captured graphs need no new params)
+    int probe_cap, parity;     // parity = index of the source buffer
     // FINAL (materialize) outputs, packed over [ox0,ox1) x [oy0,oy1)
     double *o_f, *o_rho, *o_u;
     int ox0, oy0, ow;          // ow = oy1 - oy0
@@ -319,6 +321,17 @@ __device__ __forceinline__ void halo_signal(const StepParams &P)
 //   FINAL: stop after the moments and write reference-layout f_post / rho / u (materialize)
 //   LIST : cells come from a compact list (edge fix-up kernel) instead of a row range
 // -------------------------------------------------------------------------------------------------------
+// Probe (experiments.py:703-704): the one thread that owns the probe cell appends (ux, uy) of the new time to the
+// ring and advances the device-side time counter of the destination buffer.
+__device__ __forceinline__ void record_probe(const StepParams &P, double ux, double uy)
+{
+    const long long t_new = P.tcount[P.parity] + 1;
+    double *slot = P.probe + 2 * (t_new % P.probe_cap);
+    slot[0] = ux;
+    slot[1] = uy;
+    P.tcount[P.parity ^ 1] = t_new;
+}
+
 // Everything one cell does after its nine f_post values are known (shared by the register-resident fluid path
 // and the out-of-line rule path).
 template <bool HALO, bool FINAL>
@@ -340,10 +353,7 @@ __device__ __forceinline__ void finish_cell(const StepParams &P, int x, int y, c
         }
         return;
     }
-    if (P.probe_slot && x == P.px && y == P.py) {
-        P.probe_slot[0] = ux;
-        P.probe_slot[1] = uy;
-    }
+    if (P.probe && x == P.px && y == P.py) record_probe(P, ux, uy);
     double p[9], e[9], s[9];
     eq_poly(ux, uy, p);
     eq_from_poly(rho, p, e);
@@ -467,10 +477,7 @@ __global__ void __launch_bounds__(256) k_step_pair(const __grid_constant__ StepP
     {
         double rho, ux, uy, p[9], e[9];
         moments(fa, rho, ux, uy);
-        if (P.probe_slot && x == P.px && y == P.py) {
-            P.probe_slot[0] = ux;
-            P.probe_slot[1] = uy;
-        }
+        if (P.probe && x == P.px && y == P.py) record_probe(P, ux, uy);
         eq_poly(ux, uy, p);
         eq_from_poly(rho, p, e);
         collide(fa, e, P.omega, sa);
@@ -478,10 +485,7 @@ __global__ void __launch_bounds__(256) k_step_pair(const __grid_constant__ StepP
     {
         double rho, ux, uy, p[9], e[9];
         moments(fb, rho, ux, uy);
-        if (P.probe_slot && x == P.px && y + 1 == P.py) {
-            P.probe_slot[0] = ux;
-            P.probe_slot[1] = uy;
-        }
+        if (P.probe && x == P.px && y + 1 == P.py) record_probe(P, ux, uy);
         eq_poly(ux, uy, p);
         eq_from_poly(rho, p, e);
         collide(fb, e, P.omega, sb);
@@ -736,6 +740,17 @@ struct lbm_ctx {
     // probe ring
     int px = -1, py = -1, probe_cap = 0;
     double *probe = nullptr;
+    long long *tcount = nullptr;   // device [2]
+    // CUDA graphs of kGraphSteps steps for launch-bound lattices, keyed by (omega, parity, probe, bc mode)
+    struct GraphEntry {
+        double omega;
+        int parity, mode;
+        const void *probe;
+        cudaGraphExec_t exec;
+        long long launches;
+    };
+    std::vector<GraphEntry> graphs;
+    bool use_graphs = true;
     // state
     int cur = 0;              // S[cur] = S_t
     bool loaded = false;
@@ -750,6 +765,7 @@ struct lbm_ctx {
     cudaEvent_t ev_main = nullptr, ev_edge = nullptr;
 };
 
+static void drop_graphs(lbm_ctx *c);
 static const long long kEdgeThreshold = 1 << 20;   // cells; LBM_BC_AUTO switches to the edge kernel above this
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -923,6 +939,7 @@ extern "C" int lbm_destroy(lbm_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->stream_edge) cudaStreamSynchronize(c->stream_edge);
+    drop_graphs(c);
     for (int s = 0; s < 9; s++)
         if (c->peer[s].mapped) {
             bool shared = false;   // one mapping may serve several slots
@@ -930,7 +947,7 @@ extern "C" int lbm_destroy(lbm_ctx *c)
             if (!shared) cudaIpcCloseMemHandle(c->peer[s].mapped);
         }
     void *bufs[] = {c->arena,  c->kind_map, c->kinds,    c->ktab,   c->ctab,  c->outbuf[0],   c->outbuf[1], c->cells, c->snap_row, c->snap_col,
-                    c->done_counter, c->err_flag, c->stage_f, c->stage_rho, c->stage_u, c->mm_acc, c->probe};
+                    c->done_counter, c->err_flag, c->stage_f, c->stage_rho, c->stage_u, c->mm_acc, c->probe, c->tcount};
     for (void *b : bufs)
         if (b) cudaFree(b);
     if (c->ev_main) cudaEventDestroy(c->ev_main);
@@ -973,6 +990,8 @@ static int ctx_build(lbm_ctx *c, const lbm_bc_desc *bc)
     CK(cudaMemset(c->done_counter, 0, 8));
     CK(cudaMemset(c->err_flag, 0, 4));
     CK(cudaMalloc(&c->mm_acc, 32));
+    CK(cudaMalloc(&c->tcount, 16));
+    CK(cudaMemset(c->tcount, 0, 16));
     for (int b = 0; b < 2; b++) {
         CK(cudaMalloc(&c->outbuf[b], (size_t)3 * c->pitch * 8));
         CK(cudaMemset(c->outbuf[b], 0, (size_t)3 * c->pitch * 8));
@@ -1054,6 +1073,7 @@ extern "C" int lbm_create(int device, int nx, int ny, int ghost_x, int ghost_y, 
     c->pitch = (ny + 15) & ~15;
     c->plane = (long long)nx * c->pitch;
     if (const char *g = getenv("LBM_GENERIC_KERNEL")) c->force_generic = atoi(g) != 0;
+    if (const char *g = getenv("LBM_NO_GRAPHS")) c->use_graphs = atoi(g) == 0;
     if (const char *t = getenv("LBM_HALO_TIMEOUT_S")) c->timeout_cycles = (long long)(atof(t) * 2e9);
     if (int rc = ctx_build(c, bc)) {
         std::string keep = g_err;
@@ -1197,10 +1217,14 @@ static int one_step(lbm_ctx *c, int src, double omega, long long t_new)
     const bool halo = c->halo_ready;
     const bool remote = halo && c->any_remote;
     fill_halo(c, P, dst, true);
+    (void)t_new;
+    P.parity = src;
     if (c->probe && c->px >= 0) {
         P.px = c->px;
         P.py = c->py;
-        P.probe_slot = c->probe + 2 * (t_new % c->probe_cap);
+        P.probe = c->probe;
+        P.probe_cap = c->probe_cap;
+        P.tcount = c->tcount;
     }
     const int xlo = c->gx, xhi = c->NX - c->gx;   // interior rows [xlo, xhi)
     // Flag protocol (remote neighbours only): a kernel that reads my ghosts / writes a neighbour's ghosts first
@@ -1278,6 +1302,7 @@ static int begin_load(lbm_ctx *c, double omega, InitParams &Q)
 
 static int end_load(lbm_ctx *c, double omega)
 {
+    CK(cudaMemsetAsync(c->tcount, 0, 16, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->loaded = true;
     c->t = 0;
@@ -1332,6 +1357,48 @@ extern "C" int lbm_init_equilibrium(lbm_ctx *c, const double *rho_x, const doubl
     return end_load(c, omega);
 }
 
+// ---- CUDA graphs for launch-bound lattices ----------------------------------------------------------------
+// Configs 1-4 of BASELINE.json are <= 77 k cells: a step is 2-5 us of GPU work behind ~2 us of launch gap. A graph of
+// kGraphSteps captured steps is replayed instead; kGraphSteps is even, so the A/B parity is the same before and after.
+static const int kGraphSteps = 32;
+
+static void drop_graphs(lbm_ctx *c)
+{
+    for (auto &g : c->graphs) cudaGraphExecDestroy(g.exec);
+    c->graphs.clear();
+}
+
+static int graph_for(lbm_ctx *c, double omega, lbm_ctx::GraphEntry **out)
+{
+    const int mode = c->bc_mode;
+    for (auto &g : c->graphs)
+        if (g.omega == omega && g.parity == c->cur && g.mode == mode && g.probe == (const void *)c->probe) {
+            *out = &g;
+            return LBM_OK;
+        }
+    if (c->graphs.size() >= 8) drop_graphs(c);
+    cudaGraph_t graph = nullptr;
+    const long long l0 = c->launches;
+    CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = LBM_OK, src = c->cur;
+    for (int i = 0; i < kGraphSteps && rc == LBM_OK; i++, src ^= 1) rc = one_step(c, src, omega, 0);
+    cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    const long long per_graph = c->launches - l0;
+    c->launches = l0;
+    if (rc != LBM_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+    }
+    if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "graph instantiation failed: %s", cudaGetErrorString(e));
+    c->graphs.push_back({omega, c->cur, mode, (const void *)c->probe, exec, per_graph});
+    *out = &c->graphs.back();
+    return LBM_OK;
+}
+
 extern "C" int lbm_step(lbm_ctx *c, double omega, int n_steps)
 {
     if (!c) return fail(LBM_ERR_ARG, "lbm_step: null context");
@@ -1347,7 +1414,18 @@ extern "C" int lbm_step(lbm_ctx *c, double omega, int n_steps)
         if (int rc = one_step(c, c->cur ^ 1, omega, c->t)) return rc;
         c->omega = omega;
     }
-    for (int i = 0; i < n_steps; i++) {
+    int left = n_steps;
+    if (c->use_graphs && !c->any_remote && (long long)c->NX * c->NY < kEdgeThreshold && left >= 2 * kGraphSteps) {
+        lbm_ctx::GraphEntry *g = nullptr;
+        if (int rc = graph_for(c, omega, &g)) return rc;
+        while (left >= kGraphSteps) {
+            CK(cudaGraphLaunch(g->exec, c->stream));
+            c->launches += g->launches;
+            c->t += kGraphSteps;
+            left -= kGraphSteps;
+        }
+    }
+    for (int i = 0; i < left; i++) {
         if (int rc = one_step(c, c->cur, omega, c->t + 1)) return rc;
         c->cur ^= 1;
         c->t++;
@@ -1462,6 +1540,9 @@ extern "C" int lbm_probe_config(lbm_ctx *c, int x, int y, int capacity)
     c->px = x;
     c->py = y;
     c->probe_cap = capacity;
+    const long long tt[2] = {c->t, c->t};
+    CK(cudaMemcpy(c->tcount, tt, 16, cudaMemcpyHostToDevice));
+    drop_graphs(c);
     return LBM_OK;
 }
 
