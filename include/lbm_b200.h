@@ -107,10 +107,20 @@ enum {
     LBM_BC_EDGE = 2       /* mask-free periodic kernel over all cells + thin fix-up kernel over the non-fluid cells */
 };
 
+/* ghost_x: 0 (periodic wrap in-kernel), 1 (the reference's ghost ring) or 2 (two-row slabs of a fluid lattice for
+ * the two-steps-per-pass kernel; needs ghost_y = 0 and no boundary description); ghost_y: 0 or 1. */
 int lbm_create(int device, int nx, int ny, int ghost_x, int ghost_y, const lbm_bc_desc *bc /* may be NULL */,
                lbm_ctx **out);
 int lbm_destroy(lbm_ctx *ctx);
 int lbm_set_bc_mode(lbm_ctx *ctx, int mode);
+/* Scheduling switches for A/B measurements (all default to 1 except generic_kernel):
+ *   "fused"          two time steps per pass on bandwidth-bound fluid lattices (temporal blocking)
+ *   "graphs"         CUDA-graph replay of 32 captured steps on launch-bound lattices
+ *   "generic_kernel" force the one-cell-per-thread step kernel
+ *   "fused_exact"    (default 0) an even lbm_step(n) is exactly n/2 two-step passes without the one-step tail that
+ *                    normally ends every call; results cannot be materialised until one more single step is taken
+ * Environment overrides at lbm_create: LBM_NO_FUSED=1, LBM_NO_GRAPHS=1, LBM_GENERIC_KERNEL=1. */
+int lbm_set_option(lbm_ctx *ctx, const char *name, int value);
 /* bytes of device memory the context holds */
 int64_t lbm_device_bytes(const lbm_ctx *ctx);
 /* the cudaStream_t the step kernels are launched on (for CUDA-event timing by the caller) */

@@ -71,6 +71,7 @@ SIGNATURES = {
     'lbm_create': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(BcDesc), C.POINTER(_CTX)]),
     'lbm_destroy': (C.c_int, [_CTX]),
     'lbm_set_bc_mode': (C.c_int, [_CTX, C.c_int]),
+    'lbm_set_option': (C.c_int, [_CTX, C.c_char_p, C.c_int]),
     'lbm_device_bytes': (C.c_int64, [_CTX]),
     'lbm_stream': (C.c_void_p, [_CTX]),
     'lbm_upload': (C.c_int, [_CTX, _DP, _DP, _DP, C.c_double]),

@@ -75,6 +75,7 @@ struct StepParams {
     // rows handled by this launch: [row0a, row0a+na) then [row0b, ...)
     int row0a, na, row0b;
     int bpr;           // blocks per row
+    int seg, nb;       // k_step2x: output rows per block; length of the second row range
     int y0, y1;        // columns handled: [y0, y1)
     double omega;
     const uint8_t *kind_map;   // [x*pitch + y] or null
@@ -117,7 +118,8 @@ __device__ __forceinline__ double ldS(const double *p) { return __ldcg(p); }   /
 __device__ __forceinline__ double ld_cell(const StepParams &P, int i, int xs, int ys)
 {
     if (P.use_snap) {
-        if (P.gx && (xs == 0 || xs == P.NX - 1)) return P.snap_row[((xs ? 1 : 0) * 9 + i) * (long long)P.pitch + ys];
+        // the ghost row next to the interior (row gx-1 / NX-gx) is the only one an interior cell ever pulls from
+        if (P.gx && (xs == P.gx - 1 || xs == P.NX - P.gx)) return P.snap_row[((xs >= P.gx ? 1 : 0) * 9 + i) * (long long)P.pitch + ys];
         if (P.gy && (ys == 0 || ys == P.NY - 1)) return P.snap_col[((ys ? 1 : 0) * 9 + i) * (long long)P.NX + xs];
     }
     return ldS(P.src + i * P.plane + (long long)xs * P.pitch + ys);
@@ -135,7 +137,7 @@ __device__ __forceinline__ void snapshot_ghosts(const StepParams &P, int x, int 
 #pragma unroll 1
     for (int side = 0; side < 2; side++) {
         if (side ? xh : xl) {
-            const int gx_row = side ? P.NX - 1 : 0;
+            const int gx_row = side ? P.NX - P.gx : P.gx - 1;
             const double *src = P.src + (long long)gx_row * P.pitch;
             double *dst = P.snap_row + (long long)side * 9 * P.pitch;
             for (int i = 0; i < 9; i++) {
@@ -251,7 +253,8 @@ __device__ __forceinline__ void store_pbc(const StepParams &P, unsigned flags, i
 // also writes its nine post-collision populations into the ghost cell(s) of the neighbour(s) that mirror it.
 __device__ __forceinline__ void store_halo(const StepParams &P, int x, int y, const double (&s)[9])
 {
-    const int ex_lo = (P.gx && x == P.gx), ex_hi = (P.gx && x == P.NX - 1 - P.gx);
+    // an interior cell within gx rows of a block edge mirrors into the neighbour's ghost row at the same depth
+    const int ex_lo = (P.gx && x < 2 * P.gx), ex_hi = (P.gx && x >= P.NX - 2 * P.gx);
     const int ey_lo = (P.gy && y == P.gy), ey_hi = (P.gy && y == P.NY - 1 - P.gy);
     if (!(ex_lo | ex_hi | ey_lo | ey_hi)) return;
 #pragma unroll 1
@@ -264,7 +267,7 @@ __device__ __forceinline__ void store_halo(const StepParams &P, int x, int y, co
             const HaloTarget &T = P.halo[ix * 3 + iy];
             if (!T.base) continue;
             // my first interior row is the low neighbour's high ghost row, and so on
-            const int tx = ix == 0 ? T.nx - 1 : (ix == 2 ? 0 : x);
+            const int tx = ix == 0 ? T.nx - 2 * P.gx + x : (ix == 2 ? x - (P.NX - 2 * P.gx) : x);
             const int ty = iy == 0 ? T.ny - 1 : (iy == 2 ? 0 : y);
             double *d = T.base + (long long)tx * T.pitch + ty;
 #pragma unroll
@@ -286,7 +289,7 @@ __device__ __forceinline__ void halo_wait(const StepParams &P)
             if (!P.flag_out[s]) continue;   // not a remote neighbour
             while ((int)(P.flag_in[s] - P.wait_value) < 0) {
                 if (clock64() - t0 > P.timeout_cycles) {   // a peer is not stepping in lockstep
-                    atomicExch(P.err_flag, 1u);
+                    atomicExch(P.err_flag, 0x80000000u | (P.wait_value << 8) | (unsigned)s);   // who waited for what
                     break;
                 }
                 __nanosleep(200);
@@ -496,6 +499,118 @@ __global__ void __launch_bounds__(256) k_step_pair(const __grid_constant__ StepP
 }
 
 // -------------------------------------------------------------------------------------------------------
+// TWO time steps per pass (temporal blocking) on fluid rows: S_t -> S_{t+2} with 72 B of DRAM traffic per cell
+// update instead of 144 B. A block owns output rows [x0, x1) x columns [y0, y0 + T-2) and marches along x:
+//   iteration j: pull row j of S_t from global (exactly the loads of the one-step kernel, prefetched one row
+//                ahead), collide -> row j of the INTERMEDIATE state S_{t+1} goes into a 4-slot shared-memory ring;
+//                one __syncthreads; then row j-1 of S_{t+2} is pulled from ring rows j-2, j-1, j (the +-1 column
+//                shifts are shared-memory offsets), collided and stored to global.
+// Redundant work: one intermediate column each side of the strip (2/(T-2)) and one intermediate row each end of
+// the segment (2/seg). Same per-cell arithmetic as every other kernel (lbm_device.cuh), hence the same bits as two
+// one-step launches (tests). Ghost rows of two-row slabs (gx = 2) supply the dependency cone across GPUs.
+// -------------------------------------------------------------------------------------------------------
+template <int T, bool HALO>
+__global__ void __launch_bounds__(T) k_step2x(const __grid_constant__ StepParams P)
+{
+    extern __shared__ double ring[];   // [4][9][T]
+    if (HALO) halo_wait(P);
+    constexpr int W = T - 2;
+    const int tid = threadIdx.x;
+    const int y0 = blockIdx.x * W;
+    const int rb = blockIdx.y;         // segments of the first row range, then of the second one
+    int x0, x1;
+    {
+        const int nsa = (P.na + P.seg - 1) / P.seg;
+        if (rb < nsa) {
+            x0 = P.row0a + rb * P.seg;
+            x1 = min(x0 + P.seg, P.row0a + P.na);
+        } else {
+            x0 = P.row0b + (rb - nsa) * P.seg;
+            x1 = min(x0 + P.seg, P.row0b + P.nb);
+        }
+    }
+    int c = y0 - 1 + tid;               // column of the intermediate state this thread computes
+    c = c < 0 ? c + P.NY : (c >= P.NY ? c - P.NY : c);
+    const int cm = c == 0 ? P.NY - 1 : c - 1, cp = c == P.NY - 1 ? 0 : c + 1;
+    const long long pl = P.plane;
+    const bool out_col = tid >= 1 && tid <= W && (y0 + tid - 1) < P.NY;
+    const int yo = y0 + tid - 1;        // output column
+
+    auto wrapx = [&](int r) { return r < 0 ? r + P.NX : (r >= P.NX ? r - P.NX : r); };
+    auto load = [&](int j, double (&g)[9]) {
+        const double *r0 = P.src + (long long)wrapx(j) * P.pitch, *rm = P.src + (long long)wrapx(j - 1) * P.pitch,
+                     *rp = P.src + (long long)wrapx(j + 1) * P.pitch;
+        g[0] = ldS(r0 + c);
+        g[1] = ldS(rm + pl + c);
+        g[2] = ldS(r0 + 2 * pl + cm);
+        g[3] = ldS(rp + 3 * pl + c);
+        g[4] = ldS(r0 + 4 * pl + cp);
+        g[5] = ldS(rm + 5 * pl + cm);
+        g[6] = ldS(rp + 6 * pl + cm);
+        g[7] = ldS(rp + 7 * pl + cp);
+        g[8] = ldS(rm + 8 * pl + cp);
+    };
+    const long long tc = P.probe ? P.tcount[P.parity] : 0;
+    double g[9];
+    const int j0 = x0 - 1, j1 = x1;     // intermediate rows j0..j1 inclusive
+    load(j0, g);
+    for (int j = j0; j <= j1; j++) {
+        double f[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) f[i] = g[i];
+        if (j < j1) load(j + 1, g);     // prefetch the next row while this one is computed
+        {
+            double rho, ux, uy, p[9], e[9], s[9];
+            moments(f, rho, ux, uy);
+            if (P.probe && wrapx(j) == P.px && c == P.py) {   // time t+1 (redundant rows write identical values)
+                double *slot = P.probe + 2 * ((tc + 1) % P.probe_cap);
+                slot[0] = ux;
+                slot[1] = uy;
+            }
+            eq_poly(ux, uy, p);
+            eq_from_poly(rho, p, e);
+            collide(f, e, P.omega, s);
+            double *slot = ring + (size_t)(j & 3) * 9 * T + tid;
+#pragma unroll
+            for (int i = 0; i < 9; i++) slot[i * T] = s[i];
+        }
+        __syncthreads();
+        if (j >= x0 + 1 && out_col) {   // second step: row j-1 of S_{t+2} from ring rows j-2, j-1, j
+            const double *a = ring + (size_t)((j - 2) & 3) * 9 * T + tid;
+            const double *b = ring + (size_t)((j - 1) & 3) * 9 * T + tid;
+            const double *d = ring + (size_t)(j & 3) * 9 * T + tid;
+            double h[9];
+            h[0] = b[0];
+            h[1] = a[1 * T];
+            h[2] = b[2 * T - 1];
+            h[3] = d[3 * T];
+            h[4] = b[4 * T + 1];
+            h[5] = a[5 * T - 1];
+            h[6] = d[6 * T - 1];
+            h[7] = d[7 * T + 1];
+            h[8] = a[8 * T + 1];
+            double rho, ux, uy, p[9], e[9], s[9];
+            moments(h, rho, ux, uy);
+            const int xo = wrapx(j - 1);
+            if (P.probe && xo == P.px && yo == P.py) {        // time t+2: also advances the device clock
+                double *slot = P.probe + 2 * ((tc + 2) % P.probe_cap);
+                slot[0] = ux;
+                slot[1] = uy;
+                P.tcount[P.parity ^ 1] = tc + 2;
+            }
+            eq_poly(ux, uy, p);
+            eq_from_poly(rho, p, e);
+            collide(h, e, P.omega, s);
+            double *o = P.dst + (long long)xo * P.pitch + yo;
+#pragma unroll
+            for (int i = 0; i < 9; i++) __stcg(o + i * pl, s[i]);
+            if (HALO) store_halo(P, xo, yo, s);   // no ghost snapshot: nothing is materialised from a two-step pass
+        }
+    }
+    if (HALO) halo_signal(P);
+}
+
+// -------------------------------------------------------------------------------------------------------
 // first collision of an uploaded / initialised state: S_0 = f + (feq(rho,u) - f)*omega with the GIVEN moments
 // (lattice_boltzmann_method.py:213-215). Input is either reference-layout staging (rows [x0, x0+nrows)) or the
 // separable initial fields of initial_values.py.
@@ -549,7 +664,7 @@ __global__ void __launch_bounds__(256) k_first_collide(const __grid_constant__ I
         P.out_next[2 * P.pitch + y] = f[7];
     }
     // ghost cells are owned by the neighbour that mirrors them (communicate() overwrites them before streaming)
-    const bool ghost = (P.gx && (x == 0 || x == P.NX - 1)) || (P.gy && (y == 0 || y == P.NY - 1));
+    const bool ghost = x < P.gx || x >= P.NX - P.gx || (P.gy && (y == 0 || y == P.NY - 1));
     if (!ghost) {
         store_cell(P, x, y, s, skip);
         if (flags & (LBM_CELL_PBC_IN_SRC | LBM_CELL_PBC_OUT_SRC)) store_pbc(P, flags, y, s, p, e);
@@ -751,6 +866,9 @@ struct lbm_ctx {
     };
     std::vector<GraphEntry> graphs;
     bool use_graphs = true;
+    bool use_fused = true;        // LBM_NO_FUSED=1: one step per pass only (A/B measurements)
+    bool fused_exact = false;     // tests: an even lbm_step(n) is exactly n/2 two-step passes (no one-step tail)
+    bool prev_is_tm1 = false;     // S[cur^1] holds S_{t-1} (false right after a two-step pass or a load)
     // state
     int cur = 0;              // S[cur] = S_t
     bool loaded = false;
@@ -766,6 +884,7 @@ struct lbm_ctx {
 };
 
 static void drop_graphs(lbm_ctx *c);
+static const int kFusedThreads = 256, kFusedSeg = 64;   // two-steps-per-pass kernel: threads per block, output rows per block
 static const long long kEdgeThreshold = 1 << 20;   // cells; LBM_BC_AUTO switches to the edge kernel above this
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -967,6 +1086,11 @@ static int ctx_build(lbm_ctx *c, const lbm_bc_desc *bc)
     CK(cudaStreamCreateWithPriority(&c->stream_edge, cudaStreamNonBlocking, hi));
     CK(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_edge, cudaEventDisableTiming));
+    {
+        const int smem = 4 * 9 * kFusedThreads * (int)sizeof(double);
+        CK(cudaFuncSetAttribute(k_step2x<kFusedThreads, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(k_step2x<kFusedThreads, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    }
 
     const size_t sbytes = (size_t)9 * c->plane * 8;
     c->off_S[0] = 0;
@@ -981,27 +1105,27 @@ static int ctx_build(lbm_ctx *c, const lbm_bc_desc *bc)
     c->S[0] = (double *)(c->arena + c->off_S[0]);
     c->S[1] = (double *)(c->arena + c->off_S[1]);
     c->flags_in = (unsigned *)(c->arena + c->off_flags);
-    CK(cudaMemset(c->arena + c->off_flags, 0, 256));
+    CK(cudaMemsetAsync(c->arena + c->off_flags, 0, 256, c->stream));
     // padding columns are never read, but keep the buffers defined
     CK(cudaMemsetAsync(c->S[0], 0, sbytes, c->stream));
     CK(cudaMemsetAsync(c->S[1], 0, sbytes, c->stream));
     CK(cudaMalloc(&c->done_counter, 8));
     CK(cudaMalloc(&c->err_flag, 4));
-    CK(cudaMemset(c->done_counter, 0, 8));
-    CK(cudaMemset(c->err_flag, 0, 4));
+    CK(cudaMemsetAsync(c->done_counter, 0, 8, c->stream));
+    CK(cudaMemsetAsync(c->err_flag, 0, 4, c->stream));
     CK(cudaMalloc(&c->mm_acc, 32));
     CK(cudaMalloc(&c->tcount, 16));
-    CK(cudaMemset(c->tcount, 0, 16));
+    CK(cudaMemsetAsync(c->tcount, 0, 16, c->stream));
     for (int b = 0; b < 2; b++) {
         CK(cudaMalloc(&c->outbuf[b], (size_t)3 * c->pitch * 8));
-        CK(cudaMemset(c->outbuf[b], 0, (size_t)3 * c->pitch * 8));
+        CK(cudaMemsetAsync(c->outbuf[b], 0, (size_t)3 * c->pitch * 8, c->stream));
     }
 
     if (c->gx || c->gy) {
         CK(cudaMalloc(&c->snap_row, (size_t)2 * 9 * c->pitch * 8));
-        CK(cudaMemset(c->snap_row, 0, (size_t)2 * 9 * c->pitch * 8));
+        CK(cudaMemsetAsync(c->snap_row, 0, (size_t)2 * 9 * c->pitch * 8, c->stream));
         CK(cudaMalloc(&c->snap_col, (size_t)2 * 9 * c->NX * 8));
-        CK(cudaMemset(c->snap_col, 0, (size_t)2 * 9 * c->NX * 8));
+        CK(cudaMemsetAsync(c->snap_col, 0, (size_t)2 * 9 * c->NX * 8, c->stream));
     }
 
     // staging: a chunk of rows in reference layout (96 B per cell), at most ~256 MB
@@ -1032,23 +1156,23 @@ static int ctx_build(lbm_ctx *c, const lbm_bc_desc *bc)
                         if ((kd.flags & LBM_CELL_PBC_IN_SRC) && x != c->NX - 2) return fail(LBM_ERR_ARG, "bc: PBC_IN_SRC cells must lie on row nx-2");
                         if ((kd.flags & LBM_CELL_PBC_OUT_SRC) && x != 1) return fail(LBM_ERR_ARG, "bc: PBC_OUT_SRC cells must lie on row 1");
                     }
-                    if ((c->gx && (x == 0 || x == c->NX - 1)) || (c->gy && (y == 0 || y == c->NY - 1)))
+                    if (x < c->gx || x >= c->NX - c->gx || (c->gy && (y == 0 || y == c->NY - 1)))
                         return fail(LBM_ERR_ARG, "bc: ghost cells must be fluid (the reference applies its closures to the interior view)");
                 }
             }
         if (any_pbc && (c->gx || c->NX < 4)) return fail(LBM_ERR_ARG, "bc: pressure-periodic boundary needs nx >= 4 and no ghost rows");
         CK(cudaMalloc(&c->kind_map, km.size()));
-        CK(cudaMemcpy(c->kind_map, km.data(), km.size(), cudaMemcpyHostToDevice));
+        CK(cudaMemcpyAsync(c->kind_map, km.data(), km.size(), cudaMemcpyHostToDevice, c->stream));
         CK(cudaMalloc(&c->kinds, bc->n_kinds * sizeof(lbm_kind)));
-        CK(cudaMemcpy(c->kinds, bc->kinds, bc->n_kinds * sizeof(lbm_kind), cudaMemcpyHostToDevice));
+        CK(cudaMemcpyAsync(c->kinds, bc->kinds, bc->n_kinds * sizeof(lbm_kind), cudaMemcpyHostToDevice, c->stream));
         CK(cudaMalloc(&c->ktab, bc->n_k_rows * 72));
-        CK(cudaMemcpy(c->ktab, bc->k_table, bc->n_k_rows * 72, cudaMemcpyHostToDevice));
+        CK(cudaMemcpyAsync(c->ktab, bc->k_table, bc->n_k_rows * 72, cudaMemcpyHostToDevice, c->stream));
         CK(cudaMalloc(&c->ctab, std::max(bc->n_c_rows, 1) * 72));
-        if (bc->n_c_rows) CK(cudaMemcpy(c->ctab, bc->c_table, bc->n_c_rows * 72, cudaMemcpyHostToDevice));
+        if (bc->n_c_rows) CK(cudaMemcpyAsync(c->ctab, bc->c_table, bc->n_c_rows * 72, cudaMemcpyHostToDevice, c->stream));
         c->n_cells = (int)cells.size();
         if (c->n_cells) {
             CK(cudaMalloc(&c->cells, cells.size() * sizeof(int2)));
-            CK(cudaMemcpy(c->cells, cells.data(), cells.size() * sizeof(int2), cudaMemcpyHostToDevice));
+            CK(cudaMemcpyAsync(c->cells, cells.data(), cells.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
         } else {
             c->has_bc = false;
         }
@@ -1062,8 +1186,10 @@ extern "C" int lbm_create(int device, int nx, int ny, int ghost_x, int ghost_y, 
     if (!out) return fail(LBM_ERR_ARG, "lbm_create: out is null");
     *out = nullptr;
     if (nx < 1 || ny < 1) return fail(LBM_ERR_ARG, "lbm_create: lattice must be at least 1x1 (got %dx%d)", nx, ny);
-    if ((ghost_x | ghost_y) & ~1) return fail(LBM_ERR_ARG, "lbm_create: ghost width must be 0 or 1");
-    if ((ghost_x && nx < 3) || (ghost_y && ny < 3)) return fail(LBM_ERR_ARG, "lbm_create: a ghost ring needs at least one interior cell");
+    if (ghost_x < 0 || ghost_x > 2 || (ghost_y & ~1)) return fail(LBM_ERR_ARG, "lbm_create: ghost_x must be 0, 1 or 2 and ghost_y 0 or 1");
+    if (ghost_x == 2 && (ghost_y || (bc && bc->kind_map)))
+        return fail(LBM_ERR_ARG, "lbm_create: two ghost rows (two-steps-per-pass slabs) exist for fluid lattices without y ghosts only");
+    if ((ghost_x && nx < 4 * ghost_x) || (ghost_y && ny < 3)) return fail(LBM_ERR_ARG, "lbm_create: too few interior cells for the ghost ring");
     lbm_ctx *c = new lbm_ctx;
     c->device = device;
     c->NX = nx;
@@ -1074,6 +1200,7 @@ extern "C" int lbm_create(int device, int nx, int ny, int ghost_x, int ghost_y, 
     c->plane = (long long)nx * c->pitch;
     if (const char *g = getenv("LBM_GENERIC_KERNEL")) c->force_generic = atoi(g) != 0;
     if (const char *g = getenv("LBM_NO_GRAPHS")) c->use_graphs = atoi(g) == 0;
+    if (const char *g = getenv("LBM_NO_FUSED")) c->use_fused = atoi(g) == 0;
     if (const char *t = getenv("LBM_HALO_TIMEOUT_S")) c->timeout_cycles = (long long)(atof(t) * 2e9);
     if (int rc = ctx_build(c, bc)) {
         std::string keep = g_err;
@@ -1089,6 +1216,23 @@ extern "C" int lbm_set_bc_mode(lbm_ctx *c, int mode)
 {
     if (!c || mode < LBM_BC_AUTO || mode > LBM_BC_EDGE) return fail(LBM_ERR_ARG, "lbm_set_bc_mode: bad argument");
     c->bc_mode = mode;
+    return LBM_OK;
+}
+
+extern "C" int lbm_set_option(lbm_ctx *c, const char *name, int value)
+{
+    if (!c || !name) return fail(LBM_ERR_ARG, "lbm_set_option: null argument");
+    const std::string n(name);
+    if (n == "fused")
+        c->use_fused = value != 0;
+    else if (n == "graphs")
+        c->use_graphs = value != 0;
+    else if (n == "generic_kernel")
+        c->force_generic = value != 0;
+    else if (n == "fused_exact")
+        c->fused_exact = value != 0;
+    else
+        return fail(LBM_ERR_ARG, "lbm_set_option: unknown option '%s' (fused, graphs, generic_kernel, fused_exact)", name);
     return LBM_OK;
 }
 
@@ -1231,7 +1375,8 @@ static int one_step(lbm_ctx *c, int src, double omega, long long t_new)
     // waits until every neighbour has published epoch E (= it finished producing its S_t, hence finished reading
     // the buffer I am about to overwrite), and the LAST kernel of the step that stores ghosts publishes E+1.
     const unsigned E = c->halo_epoch;
-    const bool split = halo && c->gx && !c->gy && !fix && (xhi - xlo) >= 4 && (long long)c->NX * c->NY >= kEdgeThreshold;
+    const int g = c->gx;
+    const bool split = halo && g && !c->gy && !fix && (xhi - xlo) >= 4 * g && (long long)c->NX * c->NY >= kEdgeThreshold;
     if (!split) {
         if (remote) {
             P.wait_value = E;
@@ -1248,11 +1393,11 @@ static int one_step(lbm_ctx *c, int src, double omega, long long t_new)
             Pe.wait_value = E;
             Pe.signal_value = E + 1;
         }
-        if (int rc = rows_launch(c, Pe, xlo, 1, xhi - 1, 1, mask, true, c->stream_edge)) return rc;
+        if (int rc = rows_launch(c, Pe, xlo, g, xhi - g, g, mask, true, c->stream_edge)) return rc;
         CK(cudaEventRecord(c->ev_edge, c->stream_edge));
         StepParams Pi = P;
         for (int s = 0; s < 9; s++) Pi.halo[s].base = nullptr;
-        if (int rc = rows_launch(c, Pi, xlo + 1, xhi - xlo - 2, 0, 0, mask, false, c->stream)) return rc;
+        if (int rc = rows_launch(c, Pi, xlo + g, xhi - xlo - 2 * g, 0, 0, mask, false, c->stream)) return rc;
         CK(cudaStreamWaitEvent(c->stream, c->ev_edge, 0));        // join: the next step needs both
     }
     if (fix) {
@@ -1265,6 +1410,73 @@ static int one_step(lbm_ctx *c, int src, double omega, long long t_new)
         if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "edge kernel launch failed: %s", cudaGetErrorString(e));
         c->launches++;
     }
+    if (remote) c->halo_epoch++;
+    return LBM_OK;
+}
+
+// Two reference time steps in one pass: S[src] (time t) -> S[src^1] (time t+2). Fluid lattices, no y ghosts.
+
+static bool fused_ok(const lbm_ctx *c)
+{
+    return c->use_fused && !c->has_bc && !c->gy && c->gx != 1 && c->NY >= kFusedThreads &&
+           (c->NX - 2 * c->gx) >= 8 && (long long)c->NX * c->NY >= kEdgeThreshold && (!c->gx || c->halo_ready);
+}
+
+template <bool HALO>
+static int fused_launch(lbm_ctx *c, StepParams P, int row0a, int na, int row0b, int nb, int seg, cudaStream_t st)
+{
+    if (na + nb <= 0) return LBM_OK;
+    constexpr int T = kFusedThreads;
+    const size_t smem = (size_t)4 * 9 * T * sizeof(double);
+    // (the opt-in to > 48 KB of dynamic shared memory is done once per device in ctx_build: cudaFuncSetAttribute
+    //  may wait for the device, and a neighbour's kernel may be spinning on a flag this rank has yet to publish)
+    P.row0a = row0a;
+    P.na = na;
+    P.row0b = row0b;
+    P.nb = nb;
+    P.seg = seg;
+    dim3 grid((c->NY + T - 3) / (T - 2), (na + seg - 1) / seg + (nb + seg - 1) / seg);
+    P.n_blocks = (int)(grid.x * grid.y);
+    k_step2x<T, HALO><<<grid, T, smem, st>>>(P);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "two-step kernel launch failed: %s", cudaGetErrorString(e));
+    c->launches++;
+    return LBM_OK;
+}
+
+static int two_steps(lbm_ctx *c, int src, double omega)
+{
+    const int dst = src ^ 1;
+    StepParams P;
+    fill_common(c, P, src, dst, omega);
+    P.parity = src;
+    if (c->probe && c->px >= 0) {
+        P.px = c->px;
+        P.py = c->py;
+        P.probe = c->probe;
+        P.probe_cap = c->probe_cap;
+        P.tcount = c->tcount;
+    }
+    const int g = c->gx, xlo = g, xhi = c->NX - g;
+    if (!g) return fused_launch<false>(c, P, xlo, xhi - xlo, 0, 0, kFusedSeg, c->stream);
+    // two-row slabs: the 2 + 2 edge rows (readers of the ghost rows, writers of the neighbours') first on the
+    // high-priority stream with the flag handshake, the interior overlaps with their NVLink stores
+    const bool remote = c->any_remote;
+    fill_halo(c, P, dst, true);
+    const unsigned E = c->halo_epoch;
+    CK(cudaEventRecord(c->ev_main, c->stream));
+    CK(cudaStreamWaitEvent(c->stream_edge, c->ev_main, 0));
+    StepParams Pe = P;
+    if (remote) {
+        Pe.wait_value = E;
+        Pe.signal_value = E + 1;
+    }
+    if (int rc = fused_launch<true>(c, Pe, xlo, g, xhi - g, g, g, c->stream_edge)) return rc;
+    CK(cudaEventRecord(c->ev_edge, c->stream_edge));
+    StepParams Pi = P;
+    for (int s = 0; s < 9; s++) Pi.halo[s].base = nullptr;
+    if (int rc = fused_launch<false>(c, Pi, xlo + g, xhi - xlo - 2 * g, 0, 0, kFusedSeg, c->stream)) return rc;
+    CK(cudaStreamWaitEvent(c->stream, c->ev_edge, 0));
     if (remote) c->halo_epoch++;
     return LBM_OK;
 }
@@ -1306,6 +1518,7 @@ static int end_load(lbm_ctx *c, double omega)
     CK(cudaStreamSynchronize(c->stream));
     c->loaded = true;
     c->t = 0;
+    c->prev_is_tm1 = false;
     c->omega = omega;
     // Ghost stores of the first collision are ordered against the first step by a host-side barrier the caller
     // performs (python: process-group barrier after upload); flags restart from a common epoch.
@@ -1342,12 +1555,12 @@ extern "C" int lbm_init_equilibrium(lbm_ctx *c, const double *rho_x, const doubl
     DevBuf dr, du;
     if (rho_x) {
         CK(dr.alloc((size_t)c->NX * 8));
-        CK(cudaMemcpy(dr.p, rho_x, (size_t)c->NX * 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpyAsync(dr.p, rho_x, (size_t)c->NX * 8, cudaMemcpyHostToDevice, c->stream));
         Q.rho_x = dr.as<double>();
     }
     if (ux_y) {
         CK(du.alloc((size_t)c->NY * 8));
-        CK(cudaMemcpy(du.p, ux_y, (size_t)c->NY * 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpyAsync(du.p, ux_y, (size_t)c->NY * 8, cudaMemcpyHostToDevice, c->stream));
         Q.ux_y = du.as<double>();
     }
     Q.rho0 = rho0;
@@ -1409,7 +1622,7 @@ extern "C" int lbm_step(lbm_ctx *c, double omega, int n_steps)
     CK(cudaSetDevice(c->device));
     if (omega != c->omega) {
         // S[cur] was collided with the previous call's omega. Redo that collision from the retained S_{t-1}.
-        if (c->t == 0) return fail(LBM_ERR_STATE, "omega differs from the one given at upload and no step has been taken: upload again");
+        if (c->t == 0 || !c->prev_is_tm1) return fail(LBM_ERR_STATE, "omega differs from the one the resident state was collided with and the previous state is not retained: upload again");
         if (c->any_remote) return fail(LBM_ERR_STATE, "changing omega between steps is not supported with remote halo neighbours: upload again");
         if (int rc = one_step(c, c->cur ^ 1, omega, c->t)) return rc;
         c->omega = omega;
@@ -1423,12 +1636,25 @@ extern "C" int lbm_step(lbm_ctx *c, double omega, int n_steps)
             c->launches += g->launches;
             c->t += kGraphSteps;
             left -= kGraphSteps;
+            c->prev_is_tm1 = true;
+        }
+    }
+    // Bandwidth-bound fluid lattices advance two steps per pass; the call always ENDS with a one-step launch so that
+    // the other buffer holds S_{t-1}, from which results are materialised and a changed omega is redone.
+    if (fused_ok(c) && (left >= 3 || (c->fused_exact && left >= 2))) {
+        for (int pairs = c->fused_exact && left % 2 == 0 ? left / 2 : (left - 1) / 2; pairs > 0; pairs--) {
+            if (int rc = two_steps(c, c->cur, omega)) return rc;
+            c->cur ^= 1;
+            c->t += 2;
+            left -= 2;
+            c->prev_is_tm1 = false;
         }
     }
     for (int i = 0; i < left; i++) {
         if (int rc = one_step(c, c->cur, omega, c->t + 1)) return rc;
         c->cur ^= 1;
         c->t++;
+        c->prev_is_tm1 = true;
     }
     return LBM_OK;
 }
@@ -1442,8 +1668,14 @@ extern "C" int lbm_sync(lbm_ctx *c)
     unsigned err = 0;
     CK(cudaMemcpy(&err, c->err_flag, 4, cudaMemcpyDeviceToHost));
     if (err) {
-        cudaMemset(c->err_flag, 0, 4);
-        return fail(LBM_ERR_TIMEOUT, "halo flag wait timed out: a neighbouring rank did not take the same step");
+        unsigned fl[9] = {0};
+        cudaMemcpy(fl, c->flags_in, sizeof fl, cudaMemcpyDeviceToHost);
+        cudaMemsetAsync(c->err_flag, 0, 4, c->stream);
+        cudaStreamSynchronize(c->stream);
+        return fail(LBM_ERR_TIMEOUT,
+                    "halo flag wait timed out: a neighbouring rank did not take the same step (waited for step %u of "
+                    "neighbour slot %u; flags now %u %u %u %u . %u %u %u %u; my step count %u)",
+                    (err >> 8) & 0x7fffff, err & 0xff, fl[0], fl[1], fl[2], fl[3], fl[5], fl[6], fl[7], fl[8], c->halo_epoch);
     }
     return LBM_OK;
 }
@@ -1495,7 +1727,9 @@ static int check_region(lbm_ctx *c, int x0, int x1, int y0, int y1, const char *
 {
     if (!c) return fail(LBM_ERR_ARG, "%s: null context", who);
     if (!c->loaded || c->t == 0) return fail(LBM_ERR_STATE, "%s: no step taken since the state was loaded — the caller still holds it", who);
+    if (!c->prev_is_tm1) return fail(LBM_ERR_STATE, "%s: the last launch was a two-step pass (fused_exact): take one more step first", who);
     if (x0 < 0 || y0 < 0 || x1 > c->NX || y1 > c->NY || x0 >= x1 || y0 >= y1) return fail(LBM_ERR_ARG, "%s: empty or out-of-range region", who);
+    if (c->gx == 2 && (x0 < 2 || x1 > c->NX - 2)) return fail(LBM_ERR_ARG, "%s: two-row slabs expose their interior rows [2, nx-2) only", who);
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream_edge));
     return LBM_OK;
@@ -1536,12 +1770,13 @@ extern "C" int lbm_probe_config(lbm_ctx *c, int x, int y, int capacity)
     if (c->probe) CK(cudaFree(c->probe));
     c->probe = nullptr;
     CK(cudaMalloc(&c->probe, (size_t)capacity * 16));
-    CK(cudaMemset(c->probe, 0, (size_t)capacity * 16));
+    CK(cudaMemsetAsync(c->probe, 0, (size_t)capacity * 16, c->stream));
     c->px = x;
     c->py = y;
     c->probe_cap = capacity;
     const long long tt[2] = {c->t, c->t};
-    CK(cudaMemcpy(c->tcount, tt, 16, cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(c->tcount, tt, 16, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     drop_graphs(c);
     return LBM_OK;
 }
@@ -1648,6 +1883,7 @@ extern "C" int lbm_halo_finalize(lbm_ctx *c)
     c->halo_ready = true;
     c->halo_epoch = 0;
     CK(cudaSetDevice(c->device));
-    CK(cudaMemset(c->arena + c->off_flags, 0, 256));
+    CK(cudaMemsetAsync(c->arena + c->off_flags, 0, 256, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     return LBM_OK;
 }

@@ -78,6 +78,10 @@ class Lattice:
     def launches(self):
         return int(self.lib.lbm_launch_count(self._ctx))
 
+    def set_option(self, name, value):
+        """'fused' (two steps per pass), 'graphs' (CUDA-graph replay), 'generic_kernel' — see include/lbm_b200.h."""
+        N.check(self.lib.lbm_set_option(self._ctx, name.encode(), int(value)))
+
     def load(self, f, rho, u, omega):
         """State triple of the reference (f, density, velocity) -> device; first collision with the given moments."""
         f = N.as_f64(f, (self.nx, self.ny, 9), 'f')

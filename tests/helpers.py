@@ -25,8 +25,10 @@ def assert_parity(a, b, what='', exact=True):
     if exact:
         if not np.array_equal(a, b):
             bad = np.argwhere(a != b)
+            extent = ', '.join(f'axis{k}: {int(bad[:, k].min())}..{int(bad[:, k].max())} ({len(np.unique(bad[:, k]))} distinct)'
+                               for k in range(bad.shape[1]))
             raise AssertionError(f'{what}: {len(bad)} of {a.size} values differ bitwise; first at {bad[0]}: '
-                                 f'{a[tuple(bad[0])]!r} vs {b[tuple(bad[0])]!r}; rel err {rel_err(a, b):.3e}')
+                                 f'{a[tuple(bad[0])]!r} vs {b[tuple(bad[0])]!r}; rel err {rel_err(a, b):.3e}; where: {extent}')
     else:
         m = float(np.max(np.abs(b)))
         assert rel_err(a, b) <= RTOL, f'{what}: rel err {rel_err(a, b):.3e}'

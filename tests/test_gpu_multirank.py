@@ -121,6 +121,30 @@ def test_slabs_equal_single_block():
         lat.close()
 
 
+def test_two_row_slabs_two_steps_per_pass():
+    """The bench decomposition since the two-steps-per-pass kernel: slabs with TWO ghost rows per side; edge rows
+    (2 + 2) on the edge stream with ghost stores, interior on the main stream. Must equal the single block.
+    Own process with CUDA_DEVICE_MAX_CONNECTIONS=32 (see tests/mp_slabs.py)."""
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS='32', LBM_HALO_TIMEOUT_S='10')
+    res = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'mp_slabs.py'), '--inproc', '4'],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert 'OK 4 slabs in one process' in res.stdout
+
+
+@pytest.mark.multigpu
+@pytest.mark.parametrize('size', [2, 4, 8])
+def test_two_row_slabs_one_process_per_gpu(size):
+    if _gpu_count() < size:
+        pytest.skip(f'needs {size} GPUs')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={size}',
+           '--master-addr', '127.0.0.1', '--master-port', str(29540 + size), os.path.join(ROOT, 'tests', 'mp_slabs.py')]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT,
+                         env=dict(os.environ, LBM_HALO_TIMEOUT_S='10'))
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert f'OK {size} slabs, one process per GPU' in res.stdout
+
+
 @pytest.mark.multigpu
 @pytest.mark.parametrize('size', [2, 4, 8])
 def test_one_process_per_gpu_torchrun(size):

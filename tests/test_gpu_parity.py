@@ -492,3 +492,47 @@ def test_full_size_16384_rows_equal_thin_lattice(P, oracle):
     mn_r, mx_r, mn_u, mx_u = lat.minmax()
     assert mn_r == ref[1].min() and mx_r == ref[1].max() and mn_u == ref[2].min() and mx_u == ref[2].max()
     lat.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# two steps per pass (temporal blocking) == two one-step passes
+# ---------------------------------------------------------------------------------------------------------
+def _lattice_with_env(shape, env, **kw):
+    from lattice_boltzmann_parallel_solver_b200.engine import Lattice
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return Lattice(*shape, **kw)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize('shape', [(1024, 1024), (4100, 258), (513, 2050)])
+def test_two_steps_per_pass_equals_single_steps(P, oracle, shape):
+    f, rho, u = random_state(oracle, shape, 21)
+    from lattice_boltzmann_parallel_solver_b200.engine import Lattice
+    fused = Lattice(*shape)
+    plain = _lattice_with_env(shape, {'LBM_NO_FUSED': '1'}) if shape[0] == 1024 else Lattice(*shape)
+    plain.set_option('fused', 0)
+    px, py = shape[0] // 3, shape[1] - 2
+    for lat in (fused, plain):
+        lat.probe(px, py, capacity=64)
+        lat.load(f, rho, u, 1.37)
+    l0 = fused.launches
+    for n in (7, 1, 8, 2):            # odd and even counts: 3 pairs + 1, a lone step, 3 pairs + 2, two single steps
+        fused.run(n)
+        plain.run(n)
+    assert fused.launches - l0 == (3 + 1) + 1 + (3 + 2) + 2, 'the two-step kernel was not used'
+    for a, b, nm in zip(fused.fields(), plain.fields(), 'f rho u'.split()):
+        assert_parity(a, b, f'{shape} {nm}')
+    assert_parity(fused.probe_read(1, 18), plain.probe_read(1, 18), 'probe ring')
+    if shape == (1024, 1024):
+        ref = oracle.c.run(f, rho, u, 1.37, oracle.c.periodic(), 18)
+        for a, b, nm in zip(fused.fields(), ref, 'f rho u'.split()):
+            assert_parity(a, b, f'vs oracle {nm}')
+    fused.close()
+    plain.close()
