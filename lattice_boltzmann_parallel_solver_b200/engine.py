@@ -42,11 +42,9 @@ class Lattice:
         self.omega = None
         self.time = 0                 # reference steps taken on the device since load
         self._probe = None
-        self._probe_t0 = 0
         # lazy-handle bookkeeping (see module docstring)
         self._pending = None          # omega of a step requested but not yet launched
         self._handles = {}            # api time -> list of weakrefs to LatticeArray
-        self._base = {}               # api time 0 arrays (the caller's own numpy arrays)
 
     # ---- lifetime ----------------------------------------------------------------------------------------
     def close(self):

@@ -536,3 +536,29 @@ def test_two_steps_per_pass_equals_single_steps(P, oracle, shape):
             assert_parity(a, b, f'vs oracle {nm}')
     fused.close()
     plain.close()
+
+
+def test_options_and_state_errors(P, oracle):
+    from lattice_boltzmann_parallel_solver_b200 import _native as N
+    from lattice_boltzmann_parallel_solver_b200.engine import Lattice
+    lat = Lattice(32, 32)
+    with pytest.raises(AssertionError, match='unknown option'):
+        lat.set_option('warp_drive', 1)
+    with pytest.raises(N.LbmStateError):
+        lat.run(1, 1.0)                                  # nothing loaded
+    f, rho, u = random_state(oracle, (32, 32), 1)
+    lat.load(f, rho, u, 1.0)
+    with pytest.raises(N.LbmStateError):
+        lat.fields()                                     # no step since the load: the caller still holds the state
+    with pytest.raises(N.LbmStateError):
+        lat.run(1, 1.5)                                  # omega differs from the load's and nothing to redo from
+    lat.run(2, 1.0)
+    with pytest.raises(AssertionError):
+        lat.fields(region=(0, 33, 0, 32))
+    with pytest.raises(AssertionError):
+        lat.probe(40, 0)
+    lat.close()
+    with pytest.raises(AssertionError):
+        Lattice(0, 5)
+    with pytest.raises(AssertionError):
+        Lattice(64, 64, ghost=(2, 1))
