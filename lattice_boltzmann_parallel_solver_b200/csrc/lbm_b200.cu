@@ -499,22 +499,24 @@ __global__ void __launch_bounds__(256) k_step_pair(const __grid_constant__ StepP
 }
 
 // -------------------------------------------------------------------------------------------------------
-// TWO time steps per pass (temporal blocking) on fluid rows: S_t -> S_{t+2} with 72 B of DRAM traffic per cell
-// update instead of 144 B. A block owns output rows [x0, x1) x columns [y0, y0 + T-2) and marches along x:
-//   iteration j: pull row j of S_t from global (exactly the loads of the one-step kernel, prefetched one row
-//                ahead), collide -> row j of the INTERMEDIATE state S_{t+1} goes into a 4-slot shared-memory ring;
-//                one __syncthreads; then row j-1 of S_{t+2} is pulled from ring rows j-2, j-1, j (the +-1 column
-//                shifts are shared-memory offsets), collided and stored to global.
-// Redundant work: one intermediate column each side of the strip (2/(T-2)) and one intermediate row each end of
-// the segment (2/seg). Same per-cell arithmetic as every other kernel (lbm_device.cuh), hence the same bits as two
+// TWO time steps per pass (temporal blocking) on fluid rows: S_t -> S_{t+2} with ~73 B of DRAM traffic per cell
+// update instead of 144 B. A block of T threads owns output rows [x0, x1) x columns [y0, y0 + 2T-4) and marches
+// along x; every thread owns an aligned PAIR of columns of the intermediate state S_{t+1}:
+//   iteration j: pull row j of S_t from global (exactly the loads of k_step_pair, prefetched one row ahead),
+//                collide -> row j of S_{t+1}. The six populations that move along y go into a 4-slot shared-memory
+//                ring as 128-bit stores; the three that do not (0, 1, 3) never leave the thread's registers.
+//                One __syncthreads; then row j-1 of S_{t+2} is pulled from ring rows j-2, j-1, j (the +-1 column
+//                shifts are shared-memory offsets), collided and written with 128-bit stores.
+// Redundant work: one intermediate pair each side of the strip (4/2T) and one intermediate row each end of the
+// segment (2/seg). Same per-cell arithmetic as every other kernel (lbm_device.cuh), hence the same bits as two
 // one-step launches (tests). Ghost rows of two-row slabs (gx = 2) supply the dependency cone across GPUs.
 // -------------------------------------------------------------------------------------------------------
-template <int T, bool HALO>
-__global__ void __launch_bounds__(T) k_step2x(const __grid_constant__ StepParams P)
+template <int T, bool HALO, bool PROBE>
+__global__ void __launch_bounds__(T, 4) k_step2x(const __grid_constant__ StepParams P)
 {
-    extern __shared__ double ring[];   // [4][9][T]
+    extern __shared__ double ring[];   // [4 slots][6 populations: 2,4,5,6,7,8][2T columns]
     if (HALO) halo_wait(P);
-    constexpr int W = T - 2;
+    constexpr int W = 2 * T - 4, RS = 2 * T;
     const int tid = threadIdx.x;
     const int y0 = blockIdx.x * W;
     const int rb = blockIdx.y;         // segments of the first row range, then of the second one
@@ -529,83 +531,130 @@ __global__ void __launch_bounds__(T) k_step2x(const __grid_constant__ StepParams
             x1 = min(x0 + P.seg, P.row0b + P.nb);
         }
     }
-    int c = y0 - 1 + tid;               // column of the intermediate state this thread computes
-    c = c < 0 ? c + P.NY : (c >= P.NY ? c - P.NY : c);
-    const int cm = c == 0 ? P.NY - 1 : c - 1, cp = c == P.NY - 1 ? 0 : c + 1;
+    int ca = y0 - 2 + 2 * tid;          // even column of this thread's intermediate pair (ca, ca + 1)
+    ca = ca < 0 ? ca + P.NY : (ca >= P.NY ? ca - P.NY : ca);
+    const int cm = ca == 0 ? P.NY - 1 : ca - 1;                  // left neighbour of the pair
+    const int cq = ca + 2 >= P.NY ? ca + 2 - P.NY : ca + 2;      // right neighbour of the pair
     const long long pl = P.plane;
-    const bool out_col = tid >= 1 && tid <= W && (y0 + tid - 1) < P.NY;
-    const int yo = y0 + tid - 1;        // output column
+    const int yo = y0 + 2 * tid - 2;    // first output column of this thread
+    const bool out_pair = tid >= 1 && tid <= T - 2 && yo < P.NY;
 
     auto wrapx = [&](int r) { return r < 0 ? r + P.NX : (r >= P.NX ? r - P.NX : r); };
-    auto load = [&](int j, double (&g)[9]) {
+    auto load = [&](int j, double (&ga)[9], double (&gb)[9]) {
         const double *r0 = P.src + (long long)wrapx(j) * P.pitch, *rm = P.src + (long long)wrapx(j - 1) * P.pitch,
                      *rp = P.src + (long long)wrapx(j + 1) * P.pitch;
-        g[0] = ldS(r0 + c);
-        g[1] = ldS(rm + pl + c);
-        g[2] = ldS(r0 + 2 * pl + cm);
-        g[3] = ldS(rp + 3 * pl + c);
-        g[4] = ldS(r0 + 4 * pl + cp);
-        g[5] = ldS(rm + 5 * pl + cm);
-        g[6] = ldS(rp + 6 * pl + cm);
-        g[7] = ldS(rp + 7 * pl + cp);
-        g[8] = ldS(rm + 8 * pl + cp);
+        const double2 v0 = ld2(r0 + ca), v1 = ld2(rm + pl + ca), v3 = ld2(rp + 3 * pl + ca);
+        ga[0] = v0.x; gb[0] = v0.y;
+        ga[1] = v1.x; gb[1] = v1.y;
+        ga[3] = v3.x; gb[3] = v3.y;
+        ga[2] = ldS(r0 + 2 * pl + cm); gb[2] = ldS(r0 + 2 * pl + ca);
+        ga[5] = ldS(rm + 5 * pl + cm); gb[5] = ldS(rm + 5 * pl + ca);
+        ga[6] = ldS(rp + 6 * pl + cm); gb[6] = ldS(rp + 6 * pl + ca);
+        ga[4] = ldS(r0 + 4 * pl + ca + 1); gb[4] = ldS(r0 + 4 * pl + cq);
+        ga[7] = ldS(rp + 7 * pl + ca + 1); gb[7] = ldS(rp + 7 * pl + cq);
+        ga[8] = ldS(rm + 8 * pl + ca + 1); gb[8] = ldS(rm + 8 * pl + cq);
     };
-    const long long tc = P.probe ? P.tcount[P.parity] : 0;
-    double g[9];
+    const long long tc = PROBE ? P.tcount[P.parity] : 0;
+    // register pass-through of the unshifted populations of S_{t+1}: pop 0 of row j-1, pop 1 of rows j-1 and j-2
+    double a0p = 0, b0p = 0, a1p = 0, b1p = 0, a1pp = 0, b1pp = 0;
+    double ga[9], gb[9];
     const int j0 = x0 - 1, j1 = x1;     // intermediate rows j0..j1 inclusive
-    load(j0, g);
+    load(j0, ga, gb);
     for (int j = j0; j <= j1; j++) {
-        double f[9];
+        double fa[9], fb[9];
 #pragma unroll
-        for (int i = 0; i < 9; i++) f[i] = g[i];
-        if (j < j1) load(j + 1, g);     // prefetch the next row while this one is computed
+        for (int i = 0; i < 9; i++) {
+            fa[i] = ga[i];
+            fb[i] = gb[i];
+        }
+        if (j < j1) load(j + 1, ga, gb);   // prefetch the next row while this one is computed
+        double sa[9], sb[9];
         {
-            double rho, ux, uy, p[9], e[9], s[9];
-            moments(f, rho, ux, uy);
-            if (P.probe && wrapx(j) == P.px && c == P.py) {   // time t+1 (redundant rows write identical values)
+            double rho, ux, uy, p[9], e[9];
+            const bool probe_row = PROBE && wrapx(j) == P.px;
+            moments(fa, rho, ux, uy);
+            if (probe_row && ca == P.py) {   // time t+1 (redundant rows/columns write identical values)
                 double *slot = P.probe + 2 * ((tc + 1) % P.probe_cap);
                 slot[0] = ux;
                 slot[1] = uy;
             }
             eq_poly(ux, uy, p);
             eq_from_poly(rho, p, e);
-            collide(f, e, P.omega, s);
-            double *slot = ring + (size_t)(j & 3) * 9 * T + tid;
-#pragma unroll
-            for (int i = 0; i < 9; i++) slot[i * T] = s[i];
-        }
-        __syncthreads();
-        if (j >= x0 + 1 && out_col) {   // second step: row j-1 of S_{t+2} from ring rows j-2, j-1, j
-            const double *a = ring + (size_t)((j - 2) & 3) * 9 * T + tid;
-            const double *b = ring + (size_t)((j - 1) & 3) * 9 * T + tid;
-            const double *d = ring + (size_t)(j & 3) * 9 * T + tid;
-            double h[9];
-            h[0] = b[0];
-            h[1] = a[1 * T];
-            h[2] = b[2 * T - 1];
-            h[3] = d[3 * T];
-            h[4] = b[4 * T + 1];
-            h[5] = a[5 * T - 1];
-            h[6] = d[6 * T - 1];
-            h[7] = d[7 * T + 1];
-            h[8] = a[8 * T + 1];
-            double rho, ux, uy, p[9], e[9], s[9];
-            moments(h, rho, ux, uy);
-            const int xo = wrapx(j - 1);
-            if (P.probe && xo == P.px && yo == P.py) {        // time t+2: also advances the device clock
-                double *slot = P.probe + 2 * ((tc + 2) % P.probe_cap);
+            collide(fa, e, P.omega, sa);
+            moments(fb, rho, ux, uy);
+            if (probe_row && ca + 1 == P.py) {
+                double *slot = P.probe + 2 * ((tc + 1) % P.probe_cap);
                 slot[0] = ux;
                 slot[1] = uy;
-                P.tcount[P.parity ^ 1] = tc + 2;
             }
             eq_poly(ux, uy, p);
             eq_from_poly(rho, p, e);
-            collide(h, e, P.omega, s);
+            collide(fb, e, P.omega, sb);
+        }
+        {
+            double2 *slot = reinterpret_cast<double2 *>(ring + (size_t)(j & 3) * 6 * RS) + tid;
+            slot[0 * T] = make_double2(sa[2], sb[2]);
+            slot[1 * T] = make_double2(sa[4], sb[4]);
+            slot[2 * T] = make_double2(sa[5], sb[5]);
+            slot[3 * T] = make_double2(sa[6], sb[6]);
+            slot[4 * T] = make_double2(sa[7], sb[7]);
+            slot[5 * T] = make_double2(sa[8], sb[8]);
+        }
+        __syncthreads();
+        if (j >= x0 + 1 && out_pair) {   // second step: row j-1 of S_{t+2} from intermediate rows j-2 (A), j-1 (B), j (D)
+            const double *A = ring + (size_t)((j - 2) & 3) * 6 * RS + 2 * tid;
+            const double *B = ring + (size_t)((j - 1) & 3) * 6 * RS + 2 * tid;
+            const double *D = ring + (size_t)(j & 3) * 6 * RS + 2 * tid;
+            double ha[9], hb[9];
+            ha[0] = a0p;           hb[0] = b0p;
+            ha[1] = a1pp;          hb[1] = b1pp;
+            ha[3] = sa[3];         hb[3] = sb[3];
+            ha[2] = B[0 * RS - 1]; hb[2] = B[0 * RS];
+            ha[4] = B[1 * RS + 1]; hb[4] = B[1 * RS + 2];
+            ha[5] = A[2 * RS - 1]; hb[5] = A[2 * RS];
+            ha[6] = D[3 * RS - 1]; hb[6] = D[3 * RS];
+            ha[7] = D[4 * RS + 1]; hb[7] = D[4 * RS + 2];
+            ha[8] = A[5 * RS + 1]; hb[8] = A[5 * RS + 2];
+            const int xo = wrapx(j - 1);
+            const bool probe_row = PROBE && xo == P.px;
+            double ta[9], tb[9];
+            {
+                double rho, ux, uy, p[9], e[9];
+                moments(ha, rho, ux, uy);
+                if (probe_row && yo == P.py) {        // time t+2: also advances the device clock
+                    double *slot = P.probe + 2 * ((tc + 2) % P.probe_cap);
+                    slot[0] = ux;
+                    slot[1] = uy;
+                    P.tcount[P.parity ^ 1] = tc + 2;
+                }
+                eq_poly(ux, uy, p);
+                eq_from_poly(rho, p, e);
+                collide(ha, e, P.omega, ta);
+                moments(hb, rho, ux, uy);
+                if (probe_row && yo + 1 == P.py) {
+                    double *slot = P.probe + 2 * ((tc + 2) % P.probe_cap);
+                    slot[0] = ux;
+                    slot[1] = uy;
+                    P.tcount[P.parity ^ 1] = tc + 2;
+                }
+                eq_poly(ux, uy, p);
+                eq_from_poly(rho, p, e);
+                collide(hb, e, P.omega, tb);
+            }
             double *o = P.dst + (long long)xo * P.pitch + yo;
 #pragma unroll
-            for (int i = 0; i < 9; i++) __stcg(o + i * pl, s[i]);
-            if (HALO) store_halo(P, xo, yo, s);   // no ghost snapshot: nothing is materialised from a two-step pass
+            for (int i = 0; i < 9; i++) st2(o + i * pl, ta[i], tb[i]);
+            if (HALO) {   // no ghost snapshot: nothing is materialised from a two-step pass
+                store_halo(P, xo, yo, ta);
+                store_halo(P, xo, yo + 1, tb);
+            }
         }
+        a1pp = a1p;
+        b1pp = b1p;
+        a1p = sa[1];
+        b1p = sb[1];
+        a0p = sa[0];
+        b0p = sb[0];
     }
     if (HALO) halo_signal(P);
 }
@@ -884,7 +933,7 @@ struct lbm_ctx {
 };
 
 static void drop_graphs(lbm_ctx *c);
-static const int kFusedThreads = 256, kFusedSeg = 64;   // two-steps-per-pass kernel: threads per block, output rows per block
+static const int kFusedThreads = 128, kFusedSeg = 64;   // two-steps-per-pass kernel: threads per block, output rows per block
 static const long long kEdgeThreshold = 1 << 20;   // cells; LBM_BC_AUTO switches to the edge kernel above this
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -1087,9 +1136,11 @@ static int ctx_build(lbm_ctx *c, const lbm_bc_desc *bc)
     CK(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_edge, cudaEventDisableTiming));
     {
-        const int smem = 4 * 9 * kFusedThreads * (int)sizeof(double);
-        CK(cudaFuncSetAttribute(k_step2x<kFusedThreads, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CK(cudaFuncSetAttribute(k_step2x<kFusedThreads, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        const int smem = 4 * 6 * 2 * kFusedThreads * (int)sizeof(double);
+        CK(cudaFuncSetAttribute(k_step2x<kFusedThreads, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(k_step2x<kFusedThreads, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(k_step2x<kFusedThreads, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(k_step2x<kFusedThreads, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
 
     const size_t sbytes = (size_t)9 * c->plane * 8;
@@ -1418,7 +1469,7 @@ static int one_step(lbm_ctx *c, int src, double omega, long long t_new)
 
 static bool fused_ok(const lbm_ctx *c)
 {
-    return c->use_fused && !c->has_bc && !c->gy && c->gx != 1 && c->NY >= kFusedThreads &&
+    return c->use_fused && !c->has_bc && !c->gy && c->gx != 1 && c->NY >= 2 * kFusedThreads && (c->NY % 2) == 0 &&
            (c->NX - 2 * c->gx) >= 8 && (long long)c->NX * c->NY >= kEdgeThreshold && (!c->gx || c->halo_ready);
 }
 
@@ -1427,7 +1478,7 @@ static int fused_launch(lbm_ctx *c, StepParams P, int row0a, int na, int row0b, 
 {
     if (na + nb <= 0) return LBM_OK;
     constexpr int T = kFusedThreads;
-    const size_t smem = (size_t)4 * 9 * T * sizeof(double);
+    const size_t smem = (size_t)4 * 6 * 2 * T * sizeof(double);
     // (the opt-in to > 48 KB of dynamic shared memory is done once per device in ctx_build: cudaFuncSetAttribute
     //  may wait for the device, and a neighbour's kernel may be spinning on a flag this rank has yet to publish)
     P.row0a = row0a;
@@ -1435,9 +1486,12 @@ static int fused_launch(lbm_ctx *c, StepParams P, int row0a, int na, int row0b, 
     P.row0b = row0b;
     P.nb = nb;
     P.seg = seg;
-    dim3 grid((c->NY + T - 3) / (T - 2), (na + seg - 1) / seg + (nb + seg - 1) / seg);
+    dim3 grid((c->NY + 2 * T - 5) / (2 * T - 4), (na + seg - 1) / seg + (nb + seg - 1) / seg);
     P.n_blocks = (int)(grid.x * grid.y);
-    k_step2x<T, HALO><<<grid, T, smem, st>>>(P);
+    if (P.probe)
+        k_step2x<T, HALO, true><<<grid, T, smem, st>>>(P);
+    else
+        k_step2x<T, HALO, false><<<grid, T, smem, st>>>(P);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "two-step kernel launch failed: %s", cudaGetErrorString(e));
     c->launches++;
