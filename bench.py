@@ -341,7 +341,8 @@ def main():
     if fused:
         algo_launch = 2 * per_gpu_cells * ALGO_BYTES_PER_UPDATE
         achieved = algo_launch / (2 * step_ms * 1e-3) / 1e9
-        kernel = 'k_step2x<256> (two time steps per launch through a shared-memory ring of the intermediate rows)'
+        kernel = ('k_step2x<128> (two time steps per launch: two columns per thread, shared-memory ring of the '
+                  'intermediate rows)')
     else:
         algo_launch = per_gpu_cells * ALGO_BYTES_PER_UPDATE
         achieved = algo_launch / (step_ms * 1e-3) / 1e9

@@ -5,11 +5,12 @@ set -u
 TAG=${1:-r01}
 OUT=gpurun_out
 mkdir -p $OUT
-BENCH="python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu"
+BENCH="python bench.py --steps 7 --warmup 3 --no-e2e --no-cpu"
 # 1. launch list of the bench command (cold-cache, serialised: compare SHARES)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches_${TAG}.csv $BENCH > $OUT/launches_${TAG}.log 2>&1
-# 2. full capture of the dominant kernel
-ncu --set full --clock-control none --import-source on -k regex:k_step -s 3 -c 2 -o $OUT/prof_${TAG} -f $BENCH > $OUT/prof_${TAG}.log 2>&1
+# 2. full capture of the dominant kernel (two steps per launch) and of the one-step kernel
+ncu --set full --clock-control none --import-source on -k regex:k_step2x -s 1 -c 1 -o $OUT/prof_2x_${TAG} -f $BENCH > $OUT/prof_2x_${TAG}.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_step_pair -s 1 -c 1 -o $OUT/prof_pair_${TAG} -f $BENCH --single-step > $OUT/prof_pair_${TAG}.log 2>&1
 # 3. BC-bearing workload: flag mask folded into the kernel vs mask-free kernel + edge kernel
 for mode in mask edge; do
   ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed \
