@@ -44,6 +44,7 @@ class Lattice:
         self._probe = None
         # lazy-handle bookkeeping (see module docstring)
         self._pending = None          # omega of a step requested but not yet launched
+        self._generation = 0          # bumped by every load: handles of an earlier upload never count as current
         self._handles = {}            # api time -> list of weakrefs to LatticeArray
 
     # ---- lifetime ----------------------------------------------------------------------------------------
@@ -88,6 +89,7 @@ class Lattice:
         assert 0 < omega < 2
         N.check(self.lib.lbm_upload(self._ctx, N.dptr(f), N.dptr(rho), N.dptr(u), float(omega)))
         self.omega, self.time = float(omega), 0
+        self._generation += 1
 
     def load_equilibrium(self, omega, rho_x=None, ux_y=None, rho0=1.0, ux0=0.0, uy0=0.0):
         """f = f_eq(rho, u) of a separable initial field, built on the device (initial_values.py:38-123)."""
@@ -97,6 +99,7 @@ class Lattice:
         N.check(self.lib.lbm_init_equilibrium(self._ctx, N.dptr(rx), N.dptr(uy), float(rho0), float(ux0), float(uy0),
                                               float(omega)))
         self.omega, self.time = float(omega), 0
+        self._generation += 1
 
     def run(self, n_steps, omega=None):
         """n reference time steps, asynchronous."""
@@ -200,8 +203,8 @@ class Lattice:
 
     def is_current(self, *handles):
         t = self.api_time
-        return all(isinstance(h, LatticeArray) and h._lattice is self and h._t == t and not h._dirty
-                   for h in handles)
+        return all(isinstance(h, LatticeArray) and h._lattice is self and h._generation == self._generation and
+                   h._t == t and not h._dirty for h in handles)
 
 
 def connect_blocks(blocks, dims):
@@ -231,6 +234,7 @@ class LatticeArray(np.lib.mixins.NDArrayOperatorsMixin):
 
     def __init__(self, lattice, t, which):
         self._lattice, self._t, self._which = lattice, t, which
+        self._generation = lattice._generation
         self._value = None
         self._dirty = False           # written through __setitem__: the device copy no longer matches
         self.shape = _SHAPES[which](lattice.nx, lattice.ny)
@@ -242,9 +246,9 @@ class LatticeArray(np.lib.mixins.NDArrayOperatorsMixin):
     def _bring_current(self):
         L = self._lattice
         if self._value is None:
-            if self._t == L.api_time and L._pending is not None:
+            if self._generation == L._generation and self._t == L.api_time and L._pending is not None:
                 L.flush()
-            if self._t != L.time:
+            if self._t != L.time or self._generation != L._generation:
                 raise RuntimeError('stale LatticeArray: the lattice advanced without this handle being preserved '
                                    '(internal error)')
 

@@ -1,0 +1,146 @@
+"""Host-side semantics of the lazy results of `lattice_boltzmann_step` (engine.py), on the CPU: the C library is
+replaced by tests/fake_native.py (oracle arithmetic), everything above the C-ABI is the product code. What must
+hold (SURVEY.md §8(b) "ownership"): the call is purely functional — results handed out earlier stay valid and
+unchanged however far the resident lattice has advanced; handles fed back advance the lattice without transfers."""
+import numpy as np
+import pytest
+
+from oracle import lbm_numpy as onp
+from tests.fake_native import FakeLib
+
+
+@pytest.fixture()
+def L(monkeypatch):
+    from lattice_boltzmann_parallel_solver_b200 import _native as N
+    from lattice_boltzmann_parallel_solver_b200 import lattice_boltzmann_method as L
+    fake = FakeLib()
+    monkeypatch.setattr(N, 'load', lambda: fake)
+    monkeypatch.setattr(N, 'device', lambda: 0)
+    L._lattices.clear()
+    L.fake = fake
+    yield L
+    L._lattices.clear()
+
+
+def start(shape=(12, 10), seed=0):
+    rng = np.random.default_rng(seed)
+    rho = rng.uniform(0.9, 1.1, shape)
+    u = rng.uniform(-0.05, 0.05, shape + (2,))
+    return onp.equilibrium(rho, u), rho, u
+
+
+def test_loop_is_device_resident_and_matches_the_oracle(L):
+    f, rho, u = start()
+    ref = (f, rho, u)
+    for _ in range(25):
+        f, rho, u = L.lattice_boltzmann_step(f, rho, u, 1.1)
+        ref = onp.step(*ref, 1.1)
+    lat = next(iter(L._lattices.values()))[0]
+    assert lat.time == 24 and lat._pending == 1.1            # the 25th step is deferred until somebody looks
+    assert len(L.fake.ctxs) == 1
+    before = lat.launches
+    assert np.array_equal(np.asarray(u), ref[2])             # first access: flush + one materialisation
+    assert lat.time == 25 and lat.launches == before + 2
+    assert np.array_equal(np.asarray(f), ref[0]) and np.array_equal(rho, ref[1])
+    assert lat.launches == before + 4                         # u is cached, f and rho were fetched once each
+
+
+def test_kept_results_stay_valid(L):
+    """experiments.py:254 appends every step's velocity to a list and reads them after the loop."""
+    f, rho, u = start(seed=1)
+    ref = (f, rho, u)
+    kept, kept_ref = [], []
+    for t in range(9):
+        f, rho, u = L.lattice_boltzmann_step(f, rho, u, 0.9)
+        ref = onp.step(*ref, 0.9)
+        if t % 2 == 0:
+            kept.append(u)
+            kept_ref.append(ref[2])
+    for a, b in zip(kept, kept_ref):
+        assert np.array_equal(np.asarray(a), b)
+    assert np.array_equal(np.asarray(f), ref[0])
+
+
+def test_inputs_are_never_modified_and_can_be_reused(L):
+    """experiments.py:168-176 reuses one initial tuple for all omegas."""
+    f0, rho0, u0 = start(seed=2)
+    keep = (f0.copy(), rho0.copy(), u0.copy())
+    outs = []
+    for om in (0.5, 1.0, 1.7):
+        f, rho, u = f0, rho0, u0
+        for _ in range(4):
+            f, rho, u = L.lattice_boltzmann_step(f, rho, u, om)
+        outs.append((om, f, rho, u))
+    for a, b in zip((f0, rho0, u0), keep):
+        assert np.array_equal(a, b)
+    for om, f, rho, u in outs:                               # all three runs' results are still readable
+        ref = keep
+        for _ in range(4):
+            ref = onp.step(*ref, om)
+        assert np.array_equal(np.asarray(f), ref[0]) and np.array_equal(np.asarray(u), ref[2])
+
+
+def test_cell_reads_extrema_and_ndarray_behaviour(L):
+    f, rho, u = start(seed=3)
+    ref = (f, rho, u)
+    for _ in range(3):
+        f, rho, u = L.lattice_boltzmann_step(f, rho, u, 1.2)
+        ref = onp.step(*ref, 1.2)
+        assert np.array_equal(np.array(u[4, 5, ...]), ref[2][4, 5])     # experiments.py:703
+        assert np.linalg.norm(u[4, 5, ...]) == np.linalg.norm(ref[2][4, 5])
+        assert np.amin(rho) == ref[1].min() and np.amax(u) == ref[2].max()   # experiments.py:181-193
+        assert u._value is None and rho._value is None                   # none of that materialised a field
+    assert u.shape == (12, 10, 2) and rho.ndim == 2 and len(f) == 12 and f.dtype == np.float64
+    assert np.array_equal(u[..., 0], ref[2][..., 0])                     # experiments.py:326
+    assert np.array_equal(u[1:-1, 1:-1, :], ref[2][1:-1, 1:-1, :])       # experiments.py:639
+    assert np.allclose((rho * 2 + 1).sum(), (ref[1] * 2 + 1).sum())
+    assert np.array_equal(np.stack([rho, rho]), np.stack([ref[1], ref[1]]))
+    assert float(rho.mean()) == float(ref[1].mean()) and rho.copy().flags.writeable
+    with pytest.raises(ValueError):
+        np.asarray(rho)[0, 0] = 1.0                                      # cached results are read-only views
+
+
+def test_modified_result_forces_a_fresh_upload(L):
+    f, rho, u = start(seed=4)
+    f, rho, u = L.lattice_boltzmann_step(f, rho, u, 1.0)
+    ref = onp.step(*start(seed=4), 1.0)
+    rho[0, 0] = 1.5                                                      # tracked edit through __setitem__
+    ref[1][0, 0] = 1.5
+    f2, rho2, u2 = L.lattice_boltzmann_step(f, rho, u, 1.0)
+    exp = onp.step(ref[0], ref[1], ref[2], 1.0)
+    assert np.array_equal(np.asarray(f2), exp[0])
+    lat = next(iter(L._lattices.values()))[0]
+    assert lat.time == 1                                                 # re-uploaded: the lattice restarted its clock
+
+
+def test_mixed_and_foreign_arguments_upload(L):
+    f, rho, u = start(seed=5)
+    a = L.lattice_boltzmann_step(f, rho, u, 1.0)
+    b = L.lattice_boltzmann_step(a[0], np.asarray(a[1]), a[2], 1.0)      # one plain array among handles
+    ref = onp.step(*onp.step(f, rho, u, 1.0), 1.0)
+    assert np.array_equal(np.asarray(b[0]), ref[0])
+    old = L.lattice_boltzmann_step(f, rho, u, 1.0)                       # handles of a restarted lattice ...
+    c = L.lattice_boltzmann_step(*b, 1.0)                                # ... and stale-but-materialised ones still work
+    assert np.array_equal(np.asarray(c[2]), onp.step(*ref, 1.0)[2])
+    assert np.array_equal(np.asarray(old[1]), onp.step(f, rho, u, 1.0)[1])
+
+
+def test_omega_per_call(L):
+    f, rho, u = start(seed=6)
+    ref = (f, rho, u)
+    for om in (0.3, 0.3, 1.9, 1.0):
+        f, rho, u = L.lattice_boltzmann_step(f, rho, u, om)
+        ref = onp.step(*ref, om)
+    assert np.array_equal(np.asarray(f), ref[0])
+    lat = next(iter(L._lattices.values()))[0]
+    assert L.fake._c(lat._ctx).steps_log == [0.3, 0.3, 1.9, 1.0]
+
+
+def test_direct_native_advance_makes_old_handles_loudly_stale(L):
+    f, rho, u = start(seed=7)
+    f, rho, u = L.lattice_boltzmann_step(f, rho, u, 1.0)
+    lat = next(iter(L._lattices.values()))[0]
+    lat.flush()
+    lat.run(3)                                                           # bypasses the handle protocol
+    with pytest.raises(RuntimeError, match='stale'):
+        np.asarray(u)
