@@ -1,0 +1,34 @@
+import sys
+sys.path.insert(0, '.')
+import numpy as np
+from lattice_boltzmann_parallel_solver_b200.engine import Lattice, connect_blocks
+from oracle import lbm_numpy as onp, lbm_c as oc
+# two-steps-per-pass kernel (plain and with ghost stores), mask kernel with rules, edge list kernel, materialisation
+shape = (1024, 1024)
+rng = np.random.default_rng(0)
+rho = rng.uniform(0.9, 1.1, shape); u = rng.uniform(-0.05, 0.05, shape + (2,)); f = onp.equilibrium(rho, u)
+lat = Lattice(*shape); lat.probe(100, 1022, 16); lat.load(f, rho, u, 1.2); lat.run(5)
+ref = oc.run(f, rho, u, 1.2, oc.periodic(), 5)
+print('fused ok', all(np.array_equal(a, b) for a, b in zip(lat.fields(), ref)))
+lat.close()
+n = 2052
+blk = {(0, 0): Lattice(n + 4, 512, ghost=(2, 0))}
+connect_blocks(blk, (1, 1))
+blk[(0, 0)].load_equilibrium(1.0, ux_y=0.01 * np.sin(np.arange(512) / 7.0)); blk[(0, 0)].run(5); blk[(0, 0)].sync()
+print('two-row slab (self neighbour) ran')
+blk[(0, 0)].close()
+import lattice_boltzmann_parallel_solver_b200 as P
+from lattice_boltzmann_parallel_solver_b200 import _native as N
+for mode in (N.BC_MASK, N.BC_EDGE):
+    lx, ly = 62, 40
+    bc = P.boundary_utils.parallel_von_karman_boundary_conditions([0, 0], lx, ly, lx, ly, 1, 1, 1.0, 0.1, 8)
+    r2 = rng.uniform(0.9, 1.1, (lx + 2, ly + 2)); u2 = rng.uniform(-0.05, 0.05, (lx + 2, ly + 2, 2)); f2 = onp.equilibrium(r2, u2)
+    l2 = Lattice(lx + 2, ly + 2, bc.kind_map((lx + 2, ly + 2)), ghost=(1, 1), bc_mode=mode); l2.connect_self_periodic()
+    l2.load(f2, r2, u2, 1.6); l2.run(70)
+    ref = oc.run(f2, r2, u2, 1.6, oc.karman(lx, ly, 1.0, 0.1, 8, ghost=1), 70)
+    print('karman mode', mode, all(np.array_equal(a, b) for a, b in zip(l2.fields(), ref)))
+    l2.close()
+bcp = P.boundary_utils.poiseuille_flow_boundary_conditions(40, 24, 0.3345, 0.3321)
+r3 = rng.uniform(0.9, 1.1, (40, 24)); u3 = rng.uniform(-0.05, 0.05, (40, 24, 2)); f3 = onp.equilibrium(r3, u3)
+l3 = Lattice(40, 24, bcp.kind_map((40, 24))); l3.load(f3, r3, u3, 1.5); l3.run(40)
+print('poiseuille', all(np.array_equal(a, b) for a, b in zip(l3.fields(), oc.run(f3, r3, u3, 1.5, oc.poiseuille(0.3345, 0.3321), 40))))
