@@ -260,7 +260,7 @@ def main():
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if args.impl == 'reference':
         return run_reference(args, rank)
-    assert args.warmup >= 3, 'timing hygiene: at least 3 warm-up steps'
+    args.warmup = max(args.warmup, 3)   # timing hygiene: never fewer than 3 warm-up steps
 
     import torch
     import torch.distributed as dist
@@ -397,7 +397,7 @@ def main():
     lat.close()
 
     cpu = None
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:   # CPU baseline: rank 0 at N=1 only
         k = 1
         while k * 2 <= host_cores() and args.cpu_size % (k * 2) == 0 and k * 2 <= 64:
             k *= 2

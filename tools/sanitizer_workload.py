@@ -1,3 +1,10 @@
+"""Workload for compute-sanitizer (run from the repository root on a GPU box):
+
+    compute-sanitizer --tool racecheck --racecheck-report all python tools/sanitizer_workload.py
+    compute-sanitizer --tool memcheck python tools/sanitizer_workload.py
+
+Exercises every step-kernel variant on small lattices and checks each result against the C oracle.
+"""
 import sys
 sys.path.insert(0, '.')
 import numpy as np
