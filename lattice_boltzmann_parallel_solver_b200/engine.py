@@ -48,6 +48,14 @@ class Lattice:
         self._handles = {}            # api time -> list of weakrefs to LatticeArray
 
     # ---- lifetime ----------------------------------------------------------------------------------------
+    def retire(self):
+        """Free the device lattice but keep every result that is still referenced readable (materialise first)."""
+        if self._ctx:
+            try:
+                self.reset_for_upload()
+            finally:
+                self.close()
+
     def close(self):
         if self._ctx:
             self.lib.lbm_destroy(self._ctx)
@@ -309,6 +317,8 @@ class LatticeArray(np.lib.mixins.NDArrayOperatorsMixin):
                 # velocity[px, py, ...] every step (experiments.py:703-704): fetch one cell, not the lattice
                 self._bring_current()
                 L = self._lattice
+                if not (-L.nx <= ix < L.nx and -L.ny <= iy < L.ny):
+                    raise IndexError(f'index ({ix}, {iy}) is out of bounds for a lattice of shape ({L.nx}, {L.ny})')
                 x, y = int(ix) % L.nx, int(iy) % L.ny
                 f, rho, u = L.fields(self._which == 'f', self._which == 'rho', self._which == 'u', (x, x + 1, y, y + 1))
                 cell = {'f': f, 'rho': rho, 'u': u}[self._which][0, 0]

@@ -115,15 +115,15 @@ def _lattice_for(shape, boundary, comm):
             raise TypeError('parallel_communication must come from this package\'s parallelization_utils.communication')
         attach(lat)
     if len(_lattices) > 8:     # a sweep over sizes should not pin device memory forever
-        _lattices.pop(next(iter(_lattices)))[0].close()
+        _lattices.pop(next(iter(_lattices)))[0].retire()   # results still referenced are brought to the host first
     _lattices[key] = (lat, boundary, comm)
     return lat
 
 
 def release_lattices():
-    """Frees every cached device lattice."""
+    """Frees every cached device lattice (results still referenced are brought to the host first)."""
     while _lattices:
-        _lattices.popitem()[1][0].close()
+        _lattices.popitem()[1][0].retire()
 
 
 def _flush_at_exit():

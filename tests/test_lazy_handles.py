@@ -144,3 +144,27 @@ def test_direct_native_advance_makes_old_handles_loudly_stale(L):
     lat.run(3)                                                           # bypasses the handle protocol
     with pytest.raises(RuntimeError, match='stale'):
         np.asarray(u)
+
+
+def test_cache_eviction_and_release_keep_results_readable(L):
+    results = []
+    for n in range(11):                                  # more lattice shapes than the cache holds
+        f, rho, u = start(shape=(6 + n, 5), seed=n)
+        out = L.lattice_boltzmann_step(f, rho, u, 1.0)
+        out = L.lattice_boltzmann_step(*out, 1.0)
+        results.append((out, onp.step(*onp.step(f, rho, u, 1.0), 1.0)))
+    assert len(L._lattices) <= 9
+    L.release_lattices()
+    assert not L._lattices and not L.fake.ctxs           # every device lattice is gone ...
+    for out, ref in results:                             # ... and every result handed out is still right
+        for a, b in zip(out, ref):
+            assert np.array_equal(np.asarray(a), b)
+
+
+def test_cell_index_bounds(L):
+    f, rho, u = start(seed=9)
+    f, rho, u = L.lattice_boltzmann_step(f, rho, u, 1.0)
+    ref = onp.step(*start(seed=9), 1.0)
+    assert np.array_equal(np.array(u[-1, -2]), ref[2][-1, -2])
+    with pytest.raises(IndexError):
+        u[12, 0]
