@@ -34,6 +34,12 @@ def ensure_process_group(backend=None):
     return True
 
 
+def _flush_queued_steps():
+    # a rank must not block on the host while steps of a lattice with halo neighbours are still queued
+    from . import lattice_boltzmann_method as lbm
+    lbm.flush_all()
+
+
 class WorldComm:
     """Stands where `MPI.COMM_WORLD` stands in the reference's drivers."""
 
@@ -49,6 +55,7 @@ class WorldComm:
 
     def Barrier(self):
         if self._multi:
+            _flush_queued_steps()
             _dist().barrier(self.group)
 
     barrier = Barrier
@@ -56,6 +63,7 @@ class WorldComm:
     def allgather(self, obj):
         if not self._multi:
             return [obj]
+        _flush_queued_steps()
         out = [None] * self.Get_size()
         _dist().all_gather_object(out, obj, group=self.group)
         return out
@@ -103,6 +111,7 @@ class CartComm(WorldComm):
             recvbuf[...] = sendbuf
             return
         import torch
+        _flush_queued_steps()
         dist = _dist()
         on_gpu = dist.get_backend(self.group) == 'nccl'
         dev = torch.device('cuda', torch.cuda.current_device()) if on_gpu else torch.device('cpu')

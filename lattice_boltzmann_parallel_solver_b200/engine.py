@@ -9,14 +9,19 @@ no transfer.
 
 Safety rule: the device keeps S_{t-1} and S_t (A/B buffers); values of time t are reconstructed from S_{t-1}.
 Before the device advances past t, every handle of time t that is still referenced anywhere is materialised
-(weak references tell). To make that cheap in the common loop `f, rho, u = step(f, rho, u, ...)`, the launch of
-a step is deferred until the next call or the first access: by then the loop has dropped the old handles.
+(weak references tell). To make that cheap in the common loop `f, rho, u = step(f, rho, u, ...)`, steps are
+DEFERRED: a call only queues its step (up to `MAX_DEFERRED`, same omega) and hands out the handles of the future
+time; the queue is launched when somebody looks at a result, when it is full, or when omega changes. By then the
+loop has dropped the old handles, and a whole batch goes to `lbm_step(n)` at once — which is what lets the
+reference's own driver loops run on the two-steps-per-pass kernel and on CUDA-graph replay.
 """
 import weakref
 
 import numpy as np
 
 from . import _native as N
+
+MAX_DEFERRED = 64   # steps queued by lattice_boltzmann_step before they are launched as one batch
 
 
 class Lattice:
@@ -43,7 +48,8 @@ class Lattice:
         self.time = 0                 # reference steps taken on the device since load
         self._probe = None
         # lazy-handle bookkeeping (see module docstring)
-        self._pending = None          # omega of a step requested but not yet launched
+        self._pending = None          # omega of the steps requested but not yet launched
+        self._pending_n = 0           # how many of them
         self._generation = 0          # bumped by every load: handles of an earlier upload never count as current
         self._handles = {}            # api time -> list of weakrefs to LatticeArray
 
@@ -170,7 +176,8 @@ class Lattice:
     # ---- lazy-handle protocol used by lattice_boltzmann_step ------------------------------------------------
     @property
     def api_time(self):
-        return self.time + (1 if self._pending is not None else 0)
+        """Time of the newest handles handed out (device time + queued steps)."""
+        return self.time + self._pending_n
 
     def _live(self, t):
         refs = self._handles.get(t, ())
@@ -187,17 +194,33 @@ class Lattice:
                 h._value.setflags(write=False)
         self._handles.pop(t, None)
 
-    def flush(self):
-        """Launch the deferred step, if any."""
-        if self._pending is not None:
-            omega, self._pending = self._pending, None
+    def flush(self, upto=None):
+        """Launch the queued steps (all of them, or up to api time `upto`). Times whose handles are still
+        referenced are stopped at on the way, so that those handles can be materialised before the device moves on."""
+        goal = self.api_time if upto is None else min(int(upto), self.api_time)
+        while self.time < goal:
             self._preserve(self.time)
-            self.run(1, omega)
+            stop = goal
+            for t in sorted(self._handles):
+                if self.time < t < goal and any(h._value is None for h in self._live(t)):
+                    stop = t
+                    break
+            n = stop - self.time
+            omega = self._pending
+            self._pending_n -= n
+            if self._pending_n == 0:
+                self._pending = None
+            self.run(n, omega)
+        for t in [t for t in self._handles if t < self.time and not self._live(t)]:
+            del self._handles[t]
 
     def request_step(self, omega):
-        """Called by lattice_boltzmann_step: returns the three handles of the next time."""
-        self.flush()
-        self._pending = float(omega)
+        """Called by lattice_boltzmann_step: queues one step and returns the three handles of its result."""
+        omega = float(omega)
+        if self._pending_n and (omega != self._pending or self._pending_n >= MAX_DEFERRED):
+            self.flush()
+        self._pending = omega
+        self._pending_n += 1
         t = self.api_time
         hs = tuple(LatticeArray(self, t, which) for which in ('f', 'rho', 'u'))
         self._handles[t] = [weakref.ref(h) for h in hs]
@@ -254,8 +277,8 @@ class LatticeArray(np.lib.mixins.NDArrayOperatorsMixin):
     def _bring_current(self):
         L = self._lattice
         if self._value is None:
-            if self._generation == L._generation and self._t == L.api_time and L._pending is not None:
-                L.flush()
+            if self._generation == L._generation and L.time < self._t <= L.api_time:
+                L.flush(upto=self._t)
             if self._t != L.time or self._generation != L._generation:
                 raise RuntimeError('stale LatticeArray: the lattice advanced without this handle being preserved '
                                    '(internal error)')

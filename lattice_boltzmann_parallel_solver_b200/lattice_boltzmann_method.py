@@ -126,11 +126,20 @@ def release_lattices():
         _lattices.popitem()[1][0].retire()
 
 
+def flush_all():
+    """Launch every queued step of every lattice that has halo neighbours. Called before this package's blocking
+    process-group operations (dist.WorldComm.Barrier / allgather / Sendrecv) and at interpreter exit: a neighbouring
+    rank's kernel of the same step waits for this rank's, so a rank must not block on the host with steps queued."""
+    for lat, _, comm in list(_lattices.values()):
+        if comm is not None and lat._pending_n:
+            lat.flush()
+
+
 def _flush_at_exit():
     # A rank whose loop ended with a deferred step must still launch it: neighbouring ranks' kernels of the same
     # step wait for its "begun" flag (include/lbm_b200.h, halo section).
     for lat, _, comm in list(_lattices.values()):
-        if comm is not None and lat._pending is not None:
+        if comm is not None and lat._pending_n:
             try:
                 lat.flush()
                 lat.sync()

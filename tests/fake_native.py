@@ -19,6 +19,7 @@ class _Ctx:
         self.t = 0
         self.launches = 0
         self.steps_log = []      # omegas, for assertions
+        self.calls = []          # ('step', n) / ('fields', 1) in call order
 
 
 class FakeLib:
@@ -78,6 +79,7 @@ class FakeLib:
         if c.state is None:
             self.err = b'lbm_step before lbm_upload'
             return 3
+        c.calls.append(('step', n))
         for _ in range(n):
             c.state = onp.step(*c.state, omega)
             c.t += 1
@@ -91,6 +93,7 @@ class FakeLib:
             self.err = b'no step taken since the state was loaded'
             return 3
         c.launches += 1
+        c.calls.append(('fields', 1))
         for ptr, src, tail in ((f, c.state[0], (9,)), (rho, c.state[1], ()), (u, c.state[2], (2,))):
             if ptr:
                 _arr(ptr, (x1 - x0, y1 - y0) + tail)[...] = src[x0:x1, y0:y1]

@@ -36,13 +36,13 @@ def test_loop_is_device_resident_and_matches_the_oracle(L):
         f, rho, u = L.lattice_boltzmann_step(f, rho, u, 1.1)
         ref = onp.step(*ref, 1.1)
     lat = next(iter(L._lattices.values()))[0]
-    assert lat.time == 24 and lat._pending == 1.1            # the 25th step is deferred until somebody looks
+    assert lat.time == 0 and lat._pending_n == 25 and lat._pending == 1.1   # nothing launched until somebody looks
     assert len(L.fake.ctxs) == 1
-    before = lat.launches
-    assert np.array_equal(np.asarray(u), ref[2])             # first access: flush + one materialisation
-    assert lat.time == 25 and lat.launches == before + 2
+    calls = list(L.fake._c(lat._ctx).calls)
+    assert np.array_equal(np.asarray(u), ref[2])             # first access: ONE lbm_step(25) + one materialisation
+    assert lat.time == 25 and L.fake._c(lat._ctx).calls == calls + [('step', 25), ('fields', 1)]
     assert np.array_equal(np.asarray(f), ref[0]) and np.array_equal(rho, ref[1])
-    assert lat.launches == before + 4                         # u is cached, f and rho were fetched once each
+    assert L.fake._c(lat._ctx).calls[-2:] == [('fields', 1), ('fields', 1)]   # u is cached, f and rho fetched once each
 
 
 def test_kept_results_stay_valid(L):
@@ -168,3 +168,55 @@ def test_cell_index_bounds(L):
     assert np.array_equal(np.array(u[-1, -2]), ref[2][-1, -2])
     with pytest.raises(IndexError):
         u[12, 0]
+
+
+def test_long_loops_are_launched_in_batches(L):
+    """What lets the reference's driver loops reach the two-steps-per-pass kernel / graph replay: lbm_step(n) with
+    n = MAX_DEFERRED, not n = 1."""
+    from lattice_boltzmann_parallel_solver_b200.engine import MAX_DEFERRED
+    f, rho, u = start(seed=11)
+    ref = (f, rho, u)
+    n = 3 * MAX_DEFERRED + 5
+    for _ in range(n):
+        f, rho, u = L.lattice_boltzmann_step(f, rho, u, 1.3)
+        ref = onp.step(*ref, 1.3)
+    lat = next(iter(L._lattices.values()))[0]
+    steps = [c for c in L.fake._c(lat._ctx).calls if c[0] == 'step']
+    assert steps == [('step', MAX_DEFERRED)] * 3
+    assert np.array_equal(np.asarray(rho), ref[1])
+    assert [c for c in L.fake._c(lat._ctx).calls if c[0] == 'step'][-1] == ('step', 5)
+
+
+def test_results_kept_in_the_middle_of_a_batch(L):
+    f, rho, u = start(seed=12)
+    ref = (f, rho, u)
+    kept = {}
+    for t in range(1, 41):
+        f, rho, u = L.lattice_boltzmann_step(f, rho, u, 0.7)
+        ref = onp.step(*ref, 0.7)
+        if t in (7, 8, 23):
+            kept[t] = (rho, ref[1].copy())
+        if t == 30:
+            assert np.array_equal(np.array(u[3, 3]), ref[2][3, 3])       # a look in the middle of the loop
+    lat = next(iter(L._lattices.values()))[0]
+    # the batch was split exactly where somebody still held a result: 7, 8, 23, then the look at 30
+    assert [c[1] for c in L.fake._c(lat._ctx).calls if c[0] == 'step'] == [7, 1, 15, 7]
+    for t, (h, want) in kept.items():
+        assert np.array_equal(np.asarray(h), want), t
+    assert np.array_equal(np.asarray(f), ref[0]) and lat.time == 40
+
+
+def test_old_handle_read_while_newer_steps_are_queued(L):
+    f, rho, u = start(seed=13)
+    ref = (f, rho, u)
+    hist = []
+    for t in range(10):
+        f, rho, u = L.lattice_boltzmann_step(f, rho, u, 1.0)
+        ref = onp.step(*ref, 1.0)
+        hist.append((u, ref[2]))
+    lat = next(iter(L._lattices.values()))[0]
+    assert np.array_equal(np.asarray(hist[3][0]), hist[3][1])            # advances the device to time 4 only
+    assert lat.time == 4 and lat._pending_n == 6
+    assert np.array_equal(np.asarray(hist[9][0]), hist[9][1]) and lat.time == 10
+    for h, want in hist:
+        assert np.array_equal(np.asarray(h), want)
