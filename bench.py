@@ -336,13 +336,16 @@ def main():
     # region is `pairs` two-step launches + 1-2 one-step launches, all back to back on one stream).
     peak, peak_src = measured_peak_gbs()
     per_gpu_cells = nx_local * ny
-    fused = args.workload == 'shear' and not args.single_step
+    fused = not args.single_step
     step_ms = ms / args.steps
     if fused:
         algo_launch = 2 * per_gpu_cells * ALGO_BYTES_PER_UPDATE
         achieved = algo_launch / (2 * step_ms * 1e-3) / 1e9
         kernel = ('k_step2x<128> (two time steps per launch: two columns per thread, shared-memory ring of the '
                   'intermediate rows)')
+        if args.workload == 'karman':
+            kernel += (' on the rows whose two-step dependency cone is all fluid + two one-step mask launches through '
+                       'a window on each strip of boundary rows (inlet/outlet rows, plate rows)')
     else:
         algo_launch = per_gpu_cells * ALGO_BYTES_PER_UPDATE
         achieved = algo_launch / (step_ms * 1e-3) / 1e9
@@ -367,7 +370,7 @@ def main():
             pass
     # the one-step-per-launch kernel (the north star's "reads each population once and writes it once"), timed
     # live in the same process for the same lattice
-    if fused and args.workload == 'shear':
+    if fused:
         lat.set_option('fused', 0)
         k1 = max(10, args.steps // 4)
         lat.run(3)
@@ -384,7 +387,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms1 = float(t.item())
         a1 = per_gpu_cells * ALGO_BYTES_PER_UPDATE / (ms1 / k1 * 1e-3) / 1e9
-        roofline['single_step'] = {'kernel': 'k_step_pair', 'steps': k1, 'ms_per_step': ms1 / k1,
+        roofline['single_step'] = {'kernel': 'k_step_pair' + (' + edge-list kernel' if args.workload == 'karman' else ''), 'steps': k1, 'ms_per_step': ms1 / k1,
                                    'mlups': cells_total * k1 / (ms1 * 1e-3) / 1e6, 'achieved': a1, 'frac': a1 / peak,
                                    'frac_of_nominal_8TBps': a1 / 8000.0,
                                    'traffic': tj.get('dram_bytes_per_launch_16384') if os.path.exists(prof_path) else None}

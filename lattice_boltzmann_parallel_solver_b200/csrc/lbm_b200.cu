@@ -69,7 +69,9 @@ struct HaloTarget {
 struct StepParams {
     const double *src;
     double *dst;
-    long long plane;   // NX * pitch
+    long long plane;   // plane stride of src: NX * pitch
+    long long dplane;  // plane stride of dst (differs from `plane` only when one side is a strip window)
+    int sbase, dbase;  // strip windows (two_steps on BC lattices): buffer row of lattice row x is (x - base) mod NX
     int pitch, NX, NY;
     int gx, gy;
     // rows handled by this launch: [row0a, row0a+na) then [row0b, ...)
@@ -86,8 +88,9 @@ struct StepParams {
     double rho_in, rho_out;
     int px, py;
     double *probe;             // ring of (ux, uy), probe_cap entries, or null
-    long long *tcount;         // [2]: time of the state in buffer 0 / 1 (device-resident so that captured graphs need no new params)
-    int probe_cap, parity;     // parity = index of the source buffer
+    const long long *tc_in;    // device-resident time of the state read (captured graphs need no new params) ...
+    long long *tc_out;         // ... and of the state written; both point into lbm_ctx::tcount
+    int probe_cap;
     // FINAL (materialize) outputs, packed over [ox0,ox1) x [oy0,oy1)
     double *o_f, *o_rho, *o_u;
     int ox0, oy0, ow;          // ow = oy1 - oy0
@@ -114,6 +117,11 @@ struct StepParams {
 // -------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double ldS(const double *p) { return __ldcg(p); }   // L2-coherent (peer-written ghosts)
 
+// Buffer row of lattice row x. Whole-lattice buffers have base 0; a strip window (see two_steps) holds the rows
+// base, base+1, ... (mod NX) of the lattice in its rows 0, 1, ...
+__device__ __forceinline__ long long srow(const StepParams &P, int x) { return x - P.sbase + (x < P.sbase ? P.NX : 0); }
+__device__ __forceinline__ long long drow(const StepParams &P, int x) { return x - P.dbase + (x < P.dbase ? P.NX : 0); }
+
 // Source value S[i][xs][ys]; materialisation launches take ghost cells from the snapshot (see snapshot_ghosts).
 __device__ __forceinline__ double ld_cell(const StepParams &P, int i, int xs, int ys)
 {
@@ -122,7 +130,7 @@ __device__ __forceinline__ double ld_cell(const StepParams &P, int i, int xs, in
         if (P.gx && (xs == P.gx - 1 || xs == P.NX - P.gx)) return P.snap_row[((xs >= P.gx ? 1 : 0) * 9 + i) * (long long)P.pitch + ys];
         if (P.gy && (ys == 0 || ys == P.NY - 1)) return P.snap_col[((ys ? 1 : 0) * 9 + i) * (long long)P.NX + xs];
     }
-    return ldS(P.src + i * P.plane + (long long)xs * P.pitch + ys);
+    return ldS(P.src + i * P.plane + srow(P, xs) * P.pitch + ys);
 }
 
 // Values of time t are reconstructed from S_{t-1}, ghost cells included. A neighbour that is one step ahead
@@ -159,9 +167,9 @@ __device__ __forceinline__ void pull_fluid(const StepParams &P, int x, int y, do
 {
     const int xm = x == 0 ? P.NX - 1 : x - 1, xp = x == P.NX - 1 ? 0 : x + 1;
     const int ym = y == 0 ? P.NY - 1 : y - 1, yp = y == P.NY - 1 ? 0 : y + 1;
-    const double *r0 = P.src + (long long)x * P.pitch;
-    const double *rm = P.src + (long long)xm * P.pitch;
-    const double *rp = P.src + (long long)xp * P.pitch;
+    const double *r0 = P.src + srow(P, x) * P.pitch;
+    const double *rm = P.src + srow(P, xm) * P.pitch;
+    const double *rp = P.src + srow(P, xp) * P.pitch;
     const long long pl = P.plane;
     f[0] = ldS(r0 + y);
     f[1] = ldS(rm + pl + y);
@@ -190,7 +198,7 @@ __device__ __forceinline__ double pull_rule(const StepParams &P, const lbm_kind 
         return ld_cell(P, I, xs, ys);
     }
     if (type == LBM_RULE_BOUNCE) {
-        const double v = ldS(P.src + opp[I] * pl + (long long)x * P.pitch + y);
+        const double v = ldS(P.src + opp[I] * pl + srow(P, x) * P.pitch + y);
         return row ? sub(v, P.ktab[row * 9 + opp[I]]) : v;
     }
     if (type == LBM_RULE_CONST) return P.ctab[row * 9 + I];
@@ -214,8 +222,8 @@ __device__ __forceinline__ void pull_rules(const StepParams &P, const lbm_kind &
 // Everything after the collision: stores of S' (own cell, PBC-owned virtual cells, neighbours' ghosts)
 __device__ __forceinline__ void store_cell(const StepParams &P, int x, int y, const double (&s)[9], unsigned skip)
 {
-    double *d = P.dst + (long long)x * P.pitch + y;
-    const long long pl = P.plane;
+    double *d = P.dst + drow(P, x) * P.pitch + y;
+    const long long pl = P.dplane;
     if (skip == 0) {
 #pragma unroll
         for (int i = 0; i < 9; i++) __stcg(d + i * pl, s[i]);
@@ -232,7 +240,7 @@ __device__ __forceinline__ void store_cell(const StepParams &P, int x, int y, co
 __device__ __forceinline__ void store_pbc(const StepParams &P, unsigned flags, int y, const double (&s)[9],
                                        const double (&p)[9], const double (&e)[9])
 {
-    const long long pl = P.plane;
+    const long long pl = P.dplane;   // (never launched on strip windows: lattices with this boundary have no clean rows)
     if (flags & LBM_CELL_PBC_IN_SRC) {
         const double w1 = mul(LBM_W1, P.rho_in), w5 = mul(LBM_W5, P.rho_in);
         double *d = P.dst + y;  // row 0
@@ -328,11 +336,11 @@ __device__ __forceinline__ void halo_signal(const StepParams &P)
 // ring and advances the device-side time counter of the destination buffer.
 __device__ __forceinline__ void record_probe(const StepParams &P, double ux, double uy)
 {
-    const long long t_new = P.tcount[P.parity] + 1;
+    const long long t_new = *P.tc_in + 1;
     double *slot = P.probe + 2 * (t_new % P.probe_cap);
     slot[0] = ux;
     slot[1] = uy;
-    P.tcount[P.parity ^ 1] = t_new;
+    *P.tc_out = t_new;
 }
 
 // Everything one cell does after its nine f_post values are known (shared by the register-resident fluid path
@@ -554,7 +562,7 @@ __global__ void __launch_bounds__(T, 4) k_step2x(const __grid_constant__ StepPar
         ga[7] = ldS(rp + 7 * pl + ca + 1); gb[7] = ldS(rp + 7 * pl + cq);
         ga[8] = ldS(rm + 8 * pl + ca + 1); gb[8] = ldS(rm + 8 * pl + cq);
     };
-    const long long tc = PROBE ? P.tcount[P.parity] : 0;
+    const long long tc = PROBE ? *P.tc_in : 0;
     // register pass-through of the unshifted populations of S_{t+1}: pop 0 of row j-1, pop 1 of rows j-1 and j-2
     double a0p = 0, b0p = 0, a1p = 0, b1p = 0, a1pp = 0, b1pp = 0;
     double ga[9], gb[9];
@@ -625,7 +633,7 @@ __global__ void __launch_bounds__(T, 4) k_step2x(const __grid_constant__ StepPar
                     double *slot = P.probe + 2 * ((tc + 2) % P.probe_cap);
                     slot[0] = ux;
                     slot[1] = uy;
-                    P.tcount[P.parity ^ 1] = tc + 2;
+                    *P.tc_out = tc + 2;
                 }
                 eq_poly(ux, uy, p);
                 eq_from_poly(rho, p, e);
@@ -635,7 +643,7 @@ __global__ void __launch_bounds__(T, 4) k_step2x(const __grid_constant__ StepPar
                     double *slot = P.probe + 2 * ((tc + 2) % P.probe_cap);
                     slot[0] = ux;
                     slot[1] = uy;
-                    P.tcount[P.parity ^ 1] = tc + 2;
+                    *P.tc_out = tc + 2;
                 }
                 eq_poly(ux, uy, p);
                 eq_from_poly(rho, p, e);
@@ -887,8 +895,18 @@ struct lbm_ctx {
     uint8_t *kind_map = nullptr;
     lbm_kind *kinds = nullptr;
     double *ktab = nullptr, *ctab = nullptr;
-    double *outbuf[2] = {nullptr, nullptr};
+    double *outbuf[3] = {nullptr, nullptr, nullptr};   // outlet side buffers of S[0], S[1] and of the strips' intermediate state
     double *snap_row = nullptr, *snap_col = nullptr;
+    // Two steps per pass on lattices WITH boundary cells (plan_strips): rows whose two-step dependency cone holds
+    // fluid cells only go through k_step2x; the few others are advanced by two one-step mask launches through a
+    // window that holds the intermediate state S_{t+1} of the strip (+ one row each side).
+    struct Strip {
+        int a, b;              // output rows [a, b), unwrapped: 0 <= a < NX, b may exceed NX (periodic wrap)
+        double *buf;           // [9][b - a + 2][pitch]: rows a-1 .. b of S_{t+1}
+    };
+    std::vector<Strip> strips;
+    std::vector<std::pair<int, int>> clean;   // row ranges [first, last) of k_step2x
+    bool fused_bc = false;
     int2 *cells = nullptr;
     int n_cells = 0;
     bool has_bc = false;
@@ -904,7 +922,7 @@ struct lbm_ctx {
     // probe ring
     int px = -1, py = -1, probe_cap = 0;
     double *probe = nullptr;
-    long long *tcount = nullptr;   // device [2]
+    long long *tcount = nullptr;   // device [3]: time of the state in S[0], S[1], and in the strip windows
     // CUDA graphs of kGraphSteps steps for launch-bound lattices, keyed by (omega, parity, probe, bc mode)
     struct GraphEntry {
         double omega;
@@ -1114,7 +1132,9 @@ extern "C" int lbm_destroy(lbm_ctx *c)
             for (int q = 0; q < s; q++) shared |= c->peer[q].mapped == c->peer[s].mapped;
             if (!shared) cudaIpcCloseMemHandle(c->peer[s].mapped);
         }
-    void *bufs[] = {c->arena,  c->kind_map, c->kinds,    c->ktab,   c->ctab,  c->outbuf[0],   c->outbuf[1], c->cells, c->snap_row, c->snap_col,
+    for (auto &s : c->strips)
+        if (s.buf) cudaFree(s.buf);
+    void *bufs[] = {c->arena,  c->kind_map, c->kinds,    c->ktab,   c->ctab,  c->outbuf[0],   c->outbuf[1], c->outbuf[2], c->cells, c->snap_row, c->snap_col,
                     c->done_counter, c->err_flag, c->stage_f, c->stage_rho, c->stage_u, c->mm_acc, c->probe, c->tcount};
     for (void *b : bufs)
         if (b) cudaFree(b);
@@ -1123,6 +1143,58 @@ extern "C" int lbm_destroy(lbm_ctx *c)
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->stream_edge) cudaStreamDestroy(c->stream_edge);
     delete c;
+    return LBM_OK;
+}
+
+// Which rows may take two time steps in one pass on a lattice with boundary cells? Row r of S_{t+2} is CLEAN when
+// rows r-2 .. r+2 (periodic) hold fluid cells only: then the intermediate rows r-1 .. r+1 and row r itself are plain
+// pulls, which is all k_step2x knows. Maximal runs of the other rows are STRIPS; a strip [a, b) is advanced by the
+// one-step mask kernel twice, S_t rows [a-2, b+2) -> window rows [a-1, b+1) of S_{t+1} -> S_{t+2} rows [a, b).
+// For the von Karman rule set (inlet row, plate rows, outlet rows) 13 of the NX rows are strip rows.
+static int plan_strips(lbm_ctx *c, const std::vector<int2> &cells)
+{
+    const int NX = c->NX;
+    if (NX < 16) return LBM_OK;
+    std::vector<char> dirty(NX, 0), strip_row(NX, 0);
+    for (const int2 &xy : cells) dirty[xy.x] = 1;
+    int n_strip_rows = 0;
+    for (int x = 0; x < NX; x++) {
+        for (int d = -2; d <= 2; d++) strip_row[x] |= dirty[((x + d) % NX + NX) % NX];
+        n_strip_rows += strip_row[x];
+    }
+    if (2 * n_strip_rows > NX) return LBM_OK;   // mostly boundary rows (walls along x, ...): one step per pass
+    std::vector<lbm_ctx::Strip> strips;
+    for (int a = 0; a < NX; a++) {
+        if (!strip_row[a] || strip_row[(a + NX - 1) % NX]) continue;   // a strip begins after a clean row
+        int b = a;
+        while (strip_row[b % NX]) b++;
+        strips.push_back({a, b, nullptr});
+    }
+    std::vector<std::pair<int, int>> clean;
+    for (int x = 0; x < NX;) {
+        if (strip_row[x]) {
+            x++;
+            continue;
+        }
+        int e = x;
+        while (e < NX && !strip_row[e]) e++;
+        clean.push_back({x, e});
+        x = e;
+    }
+    if (strips.size() > 16 || clean.size() > 16) return LBM_OK;
+    for (auto &s : strips) {
+        const size_t bytes = (size_t)9 * (s.b - s.a + 2) * c->pitch * 8;
+        if (cudaMalloc(&s.buf, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            for (auto &q : strips)
+                if (q.buf) cudaFree(q.buf);
+            return fail(LBM_ERR_NOMEM, "cannot allocate %.1f MB for a boundary strip window", bytes / 1e6);
+        }
+        CK(cudaMemsetAsync(s.buf, 0, bytes, c->stream));
+    }
+    c->strips = strips;
+    c->clean = clean;
+    c->fused_bc = true;
     return LBM_OK;
 }
 
@@ -1165,9 +1237,9 @@ static int ctx_build(lbm_ctx *c, const lbm_bc_desc *bc)
     CK(cudaMemsetAsync(c->done_counter, 0, 8, c->stream));
     CK(cudaMemsetAsync(c->err_flag, 0, 4, c->stream));
     CK(cudaMalloc(&c->mm_acc, 32));
-    CK(cudaMalloc(&c->tcount, 16));
-    CK(cudaMemsetAsync(c->tcount, 0, 16, c->stream));
-    for (int b = 0; b < 2; b++) {
+    CK(cudaMalloc(&c->tcount, 24));
+    CK(cudaMemsetAsync(c->tcount, 0, 24, c->stream));
+    for (int b = 0; b < 3; b++) {
         CK(cudaMalloc(&c->outbuf[b], (size_t)3 * c->pitch * 8));
         CK(cudaMemsetAsync(c->outbuf[b], 0, (size_t)3 * c->pitch * 8, c->stream));
     }
@@ -1224,6 +1296,8 @@ static int ctx_build(lbm_ctx *c, const lbm_bc_desc *bc)
         if (c->n_cells) {
             CK(cudaMalloc(&c->cells, cells.size() * sizeof(int2)));
             CK(cudaMemcpyAsync(c->cells, cells.data(), cells.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+            if (!any_pbc && !c->gx && !c->gy)
+                if (int rc = plan_strips(c, cells)) return rc;
         } else {
             c->has_bc = false;
         }
@@ -1306,6 +1380,7 @@ static void fill_common(const lbm_ctx *c, StepParams &P, int src_buf, int dst_bu
     P.src = c->S[src_buf];
     P.dst = c->S[dst_buf];
     P.plane = c->plane;
+    P.dplane = c->plane;
     P.pitch = c->pitch;
     P.NX = c->NX;
     P.NY = c->NY;
@@ -1331,6 +1406,18 @@ static void fill_common(const lbm_ctx *c, StepParams &P, int src_buf, int dst_bu
     P.timeout_cycles = c->timeout_cycles;
     P.err_flag = c->err_flag;
     P.flag_in = c->flags_in;
+}
+
+// Probe recording of a launch that reads the state whose time is tcount[tc_in] and produces tcount[tc_out]
+static void set_probe(const lbm_ctx *c, StepParams &P, int tc_in, int tc_out)
+{
+    if (!c->probe || c->px < 0) return;
+    P.px = c->px;
+    P.py = c->py;
+    P.probe = c->probe;
+    P.probe_cap = c->probe_cap;
+    P.tc_in = c->tcount + tc_in;
+    P.tc_out = c->tcount + tc_out;
 }
 
 // arena offsets of a peer (its S[1] offset depends on ITS plane size)
@@ -1413,14 +1500,7 @@ static int one_step(lbm_ctx *c, int src, double omega, long long t_new)
     const bool remote = halo && c->any_remote;
     fill_halo(c, P, dst, true);
     (void)t_new;
-    P.parity = src;
-    if (c->probe && c->px >= 0) {
-        P.px = c->px;
-        P.py = c->py;
-        P.probe = c->probe;
-        P.probe_cap = c->probe_cap;
-        P.tcount = c->tcount;
-    }
+    set_probe(c, P, src, dst);
     const int xlo = c->gx, xhi = c->NX - c->gx;   // interior rows [xlo, xhi)
     // Flag protocol (remote neighbours only): a kernel that reads my ghosts / writes a neighbour's ghosts first
     // waits until every neighbour has published epoch E (= it finished producing its S_t, hence finished reading
@@ -1469,7 +1549,7 @@ static int one_step(lbm_ctx *c, int src, double omega, long long t_new)
 
 static bool fused_ok(const lbm_ctx *c)
 {
-    return c->use_fused && !c->has_bc && !c->gy && c->gx != 1 && c->NY >= 2 * kFusedThreads && (c->NY % 2) == 0 &&
+    return c->use_fused && (!c->has_bc || c->fused_bc) && !c->gy && c->gx != 1 && c->NY >= 2 * kFusedThreads && (c->NY % 2) == 0 &&
            (c->NX - 2 * c->gx) >= 8 && (long long)c->NX * c->NY >= kEdgeThreshold && (!c->gx || c->halo_ready);
 }
 
@@ -1498,19 +1578,53 @@ static int fused_launch(lbm_ctx *c, StepParams P, int row0a, int na, int row0b, 
     return LBM_OK;
 }
 
+// Lattice with boundary cells (plan_strips): k_step2x on the clean rows, two one-step mask launches per strip.
+// All launches read S[src] (and the strip windows) and write disjoint rows of S[dst]: plain stream order.
+static int two_steps_bc(lbm_ctx *c, const StepParams &P0, int src, int dst)
+{
+    const int NX = c->NX;
+    const bool probe = c->probe && c->px >= 0;
+    for (size_t i = 0; i < c->clean.size(); i += 2) {
+        StepParams P = P0;
+        const auto ra = c->clean[i], rb = i + 1 < c->clean.size() ? c->clean[i + 1] : std::make_pair(0, 0);
+        if (probe && ((c->px >= ra.first && c->px < ra.second) || (c->px >= rb.first && c->px < rb.second))) set_probe(c, P, src, dst);
+        if (int rc = fused_launch<false>(c, P, ra.first, ra.second - ra.first, rb.first, rb.second - rb.first, kFusedSeg, c->stream)) return rc;
+    }
+    for (const auto &s : c->strips) {
+        const int base = (s.a + NX - 1) % NX;
+        const long long wplane = (long long)(s.b - s.a + 2) * c->pitch;
+        const bool probe_here = probe && ((c->px >= s.a && c->px < s.b) || (c->px + NX >= s.a && c->px + NX < s.b));
+        // rows [lo, hi) of the lattice, unwrapped, as (at most) two wrapped ranges
+        auto launch_rows = [&](StepParams &P, int lo, int hi) {
+            if (lo < 0) return rows_launch(c, P, lo + NX, -lo, 0, hi, true, false, c->stream);
+            if (hi > NX) return rows_launch(c, P, lo, NX - lo, 0, hi - NX, true, false, c->stream);
+            return rows_launch(c, P, lo, hi - lo, 0, 0, true, false, c->stream);
+        };
+        StepParams P1 = P0;   // S_t -> window: rows a-1 .. b of S_{t+1}
+        P1.dst = s.buf;
+        P1.dplane = wplane;
+        P1.dbase = base;
+        P1.out_next = c->outbuf[2];
+        if (probe_here) set_probe(c, P1, src, 2);
+        if (int rc = launch_rows(P1, s.a - 1, s.b + 1)) return rc;
+        StepParams P2 = P0;   // window -> S_{t+2} rows a .. b-1
+        P2.src = s.buf;
+        P2.plane = wplane;
+        P2.sbase = base;
+        P2.out_cur = c->outbuf[2];
+        if (probe_here) set_probe(c, P2, 2, dst);
+        if (int rc = launch_rows(P2, s.a, s.b)) return rc;
+    }
+    return LBM_OK;
+}
+
 static int two_steps(lbm_ctx *c, int src, double omega)
 {
     const int dst = src ^ 1;
     StepParams P;
     fill_common(c, P, src, dst, omega);
-    P.parity = src;
-    if (c->probe && c->px >= 0) {
-        P.px = c->px;
-        P.py = c->py;
-        P.probe = c->probe;
-        P.probe_cap = c->probe_cap;
-        P.tcount = c->tcount;
-    }
+    if (c->has_bc) return two_steps_bc(c, P, src, dst);
+    set_probe(c, P, src, dst);
     const int g = c->gx, xlo = g, xhi = c->NX - g;
     if (!g) return fused_launch<false>(c, P, xlo, xhi - xlo, 0, 0, kFusedSeg, c->stream);
     // two-row slabs: the 2 + 2 edge rows (readers of the ghost rows, writers of the neighbours') first on the
@@ -1568,7 +1682,7 @@ static int begin_load(lbm_ctx *c, double omega, InitParams &Q)
 
 static int end_load(lbm_ctx *c, double omega)
 {
-    CK(cudaMemsetAsync(c->tcount, 0, 16, c->stream));
+    CK(cudaMemsetAsync(c->tcount, 0, 24, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->loaded = true;
     c->t = 0;
@@ -1828,8 +1942,8 @@ extern "C" int lbm_probe_config(lbm_ctx *c, int x, int y, int capacity)
     c->px = x;
     c->py = y;
     c->probe_cap = capacity;
-    const long long tt[2] = {c->t, c->t};
-    CK(cudaMemcpyAsync(c->tcount, tt, 16, cudaMemcpyHostToDevice, c->stream));
+    const long long tt[3] = {c->t, c->t, c->t};
+    CK(cudaMemcpyAsync(c->tcount, tt, 24, cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     drop_graphs(c);
     return LBM_OK;

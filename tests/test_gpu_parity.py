@@ -538,6 +538,80 @@ def test_two_steps_per_pass_equals_single_steps(P, oracle, shape):
     plain.close()
 
 
+def _karman_bundle(P, shape, second_plate=False):
+    """milestone_6's rule set (inlet row, outlet rows, thin plate at nx//4) scaled to `shape`, as bench.py builds it."""
+    B, BU = P.boundary_conditions, P.boundary_utils
+    nx, ny = shape
+    d = int(ny / 4.5) // 2 * 2
+    plate = np.zeros(shape, dtype=bool)
+    plate[nx // 4, ny // 2 - d // 2:ny // 2 + d // 2] = True
+    bundle = BU.BoundaryBundle('von_karman_serial', shape)
+    bundle.add(B.inlet(shape, 1.0, 0.1)).add(B.outlet()).add(B.rigid_object(plate))
+    if second_plate:
+        plate2 = np.zeros(shape, dtype=bool)
+        plate2[5 * nx // 8, ny // 8:ny // 8 + 40] = True
+        bundle.add(B.rigid_object(plate2))
+    return bundle, d
+
+
+@pytest.mark.parametrize('shape,where,second', [((1024, 1024), 'clean', False), ((1024, 1024), 'plate', False),
+                                                ((2050, 512), 'outlet', False), ((2050, 512), 'inlet', True),
+                                                ((1024, 1024), 'next_to_strip', True)])
+def test_two_steps_per_pass_with_boundary_cells(P, oracle, shape, where, second):
+    """Lattices WITH boundary cells take two steps per pass too: k_step2x on the rows whose two-step cone is all
+    fluid, two one-step mask launches through a window on each strip of other rows (plan_strips). Must equal
+    one-step launches and the C oracle bit for bit, probe ring included, wherever the probe sits."""
+    from lattice_boltzmann_parallel_solver_b200.engine import Lattice
+    nx, ny = shape
+    bundle, d = _karman_bundle(P, shape, second)
+    f, rho, u = random_state(oracle, shape, 5)
+    px, py = {'clean': (nx // 2, ny // 3), 'plate': (nx // 4 + 1, ny // 2), 'outlet': (nx - 2, 5), 'inlet': (1, ny - 1),
+              'next_to_strip': (nx // 4 - 3, ny // 2 + 1)}[where]
+    fused = Lattice(nx, ny, bundle.kind_map(shape))
+    plain = Lattice(nx, ny, bundle.kind_map(shape))
+    plain.set_option('fused', 0)
+    for lat in (fused, plain):
+        lat.probe(px, py, capacity=64)
+        lat.load(f, rho, u, 1.41)
+    l0, p0 = fused.launches, plain.launches
+    for n in (7, 1, 8, 2):
+        fused.run(n)
+        plain.run(n)
+    strips = 3 if second else 2          # {outlet rows, inlet row} wrap into one strip; one strip per plate
+    per_pass = 1 + 2 * strips            # k_step2x over the clean ranges (two per launch) + two launches per strip
+    if second:
+        per_pass += 1                    # three clean ranges -> two k_step2x launches
+    assert plain.launches - p0 == 2 * 18
+    assert fused.launches - l0 == (3 * per_pass + 2) + 2 + (3 * per_pass + 4) + 4, 'the two-step pass was not used'
+    for a, b, nm in zip(fused.fields(), plain.fields(), 'f rho u'.split()):
+        assert_parity(a, b, f'{shape} {where} {nm}')
+    assert_parity(fused.probe_read(1, 18), plain.probe_read(1, 18), 'probe ring')
+    if not second:
+        ref = oracle.c.run(f, rho, u, 1.41, oracle.c.karman(nx, ny, 1.0, 0.1, d, ghost=0, probe=(px, py)), 18, want_probe=True)
+        for a, b, nm in zip(fused.fields(), ref, 'f rho u'.split()):
+            assert_parity(a, b, f'vs oracle {nm}')
+        assert_parity(fused.probe_read(1, 18), ref[3], 'probe vs oracle')
+    fused.close()
+    plain.close()
+
+
+def test_boundary_rows_everywhere_stay_on_one_step_per_pass(P, oracle):
+    """Walls along x make every row a boundary row: no clean rows, the two-step pass must not be chosen."""
+    from lattice_boltzmann_parallel_solver_b200.engine import Lattice
+    shape = (1024, 1024)
+    bc = P.boundary_utils.couette_flow_boundary_conditions(*shape, 0.03, 1.0)
+    f, rho, u = random_state(oracle, shape, 6)
+    lat = Lattice(*shape, bc.kind_map(shape))
+    lat.load(f, rho, u, 0.8)
+    l0 = lat.launches
+    lat.run(6)
+    assert lat.launches - l0 == 12       # mask-free kernel + edge list per step
+    ref = oracle.c.run(f, rho, u, 0.8, oracle.c.couette(0.03, 1.0), 6)
+    for a, b, nm in zip(lat.fields(), ref, 'f rho u'.split()):
+        assert_parity(a, b, f'couette 1024 {nm}')
+    lat.close()
+
+
 def test_options_and_state_errors(P, oracle):
     from lattice_boltzmann_parallel_solver_b200 import _native as N
     from lattice_boltzmann_parallel_solver_b200.engine import Lattice
