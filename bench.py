@@ -29,6 +29,16 @@ ALGO_BYTES_PER_UPDATE = 144.0   # 9 populations x 8 B read + 9 x 8 B written (SU
 EPS, OMEGA = 0.01, 1.0
 
 
+# stdout carries exactly ONE line, the JSON result: everything else that writes to file descriptor 1 while the
+# bench runs (NCCL's version banner, library chatter) is sent to stderr.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + '\n').encode())
+
+
 def measured_peak_gbs():
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as fh:
@@ -219,7 +229,7 @@ def run_reference(args, rank):
         'cpu_baseline': {'value': mlups, 'unit': 'MLUPS', 'cores': k, 'kind': 'port', 'sample': sample},
         'e2e': {'value': mlups, 'unit': 'MLUPS', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, world):
@@ -419,10 +429,10 @@ def main():
             'metric': 'D2Q9 fp64 MLUPS', 'value': mlups, 'unit': 'MLUPS', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
             'scaling': 'strong' if args.strong else 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': dict(workload_config(args, world), **({'workload': f'von Karman rule set (inlet, outlet, plate) on {args.size}x{args.size}, bc_mode={args.bc_mode}'} if args.workload == 'karman' else {})), 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
+            'config': dict(workload_config(args, world), **({'workload': f'von Karman rule set (inlet, outlet, plate) on {args.size}x{args.size}, bc_mode={args.bc_mode}', 'omega': float(np.reciprocal(3 * 0.04 + 0.5)), 'epsilon': None} if args.workload == 'karman' else {})), 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
             'roofline': roofline, 'cpu_baseline': cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -86,6 +86,13 @@ typedef struct {
     const uint8_t *kind_map;   /* nx*ny bytes, reference index order [x][y]; NULL = all fluid */
 } lbm_bc_desc;
 
+/* Test hook: compares the kernels' hand-expanded fp64 division (shared reciprocal, lbm_device.cuh) and square root
+ * with the compiler's IEEE __ddiv_rn / __dsqrt_rn on n generated operand pairs. out[0], out[1] = number of
+ * quotients / roots whose bits differ (must be 0), out[2..3] = operands of the first differing quotient,
+ * out[4] = operand of the first differing root. Guards the bit-exactness of compute_velocity_field
+ * (src/lattice_boltzmann_method.py:122-133) and of the norm in equilibrium_distr_func (:185). */
+int lbm_selftest_arith(int device, int64_t n, uint64_t seed, uint64_t out[5]);
+
 /* Applies the closures' effect to host arrays (used when a boundary closure is CALLED directly, as the
  * reference's tests/test_boundary_conditions.py does). f_post is updated in place; f_prev may be NULL when no
  * OUTLET rule is present. PBC source flags are ignored here — use lbm_pbc_apply. */
@@ -114,12 +121,16 @@ int lbm_create(int device, int nx, int ny, int ghost_x, int ghost_y, const lbm_b
 int lbm_destroy(lbm_ctx *ctx);
 int lbm_set_bc_mode(lbm_ctx *ctx, int mode);
 /* Scheduling switches for A/B measurements (all default to 1 except generic_kernel):
- *   "fused"          two time steps per pass on bandwidth-bound fluid lattices (temporal blocking)
+ *   "fused"          two time steps per pass on bandwidth-bound lattices (temporal blocking); on lattices with
+ *                    boundary cells the rows whose two-step dependency cone is all fluid take the two-step kernel,
+ *                    the other rows two one-step mask launches through a strip window (needs ghost_x = ghost_y = 0,
+ *                    no pressure-periodic rows, and boundary cells on at most half of the rows)
  *   "graphs"         CUDA-graph replay of 32 captured steps on launch-bound lattices
  *   "generic_kernel" force the one-cell-per-thread step kernel
  *   "fused_exact"    (default 0) an even lbm_step(n) is exactly n/2 two-step passes without the one-step tail that
  *                    normally ends every call; results cannot be materialised until one more single step is taken
- * Environment overrides at lbm_create: LBM_NO_FUSED=1, LBM_NO_GRAPHS=1, LBM_GENERIC_KERNEL=1. */
+ *   "fused_seg"      (default 64) output rows per thread block of the two-step kernel
+ * Environment overrides at lbm_create: LBM_NO_FUSED=1, LBM_NO_GRAPHS=1, LBM_GENERIC_KERNEL=1, LBM_FUSED_SEG=n. */
 int lbm_set_option(lbm_ctx *ctx, const char *name, int value);
 /* bytes of device memory the context holds */
 int64_t lbm_device_bytes(const lbm_ctx *ctx);

@@ -565,17 +565,14 @@ __global__ void __launch_bounds__(T, 4) k_step2x(const __grid_constant__ StepPar
     const long long tc = PROBE ? *P.tc_in : 0;
     // register pass-through of the unshifted populations of S_{t+1}: pop 0 of row j-1, pop 1 of rows j-1 and j-2
     double a0p = 0, b0p = 0, a1p = 0, b1p = 0, a1pp = 0, b1pp = 0;
-    double ga[9], gb[9];
     const int j0 = x0 - 1, j1 = x1;     // intermediate rows j0..j1 inclusive
-    load(j0, ga, gb);
+
+    // One row per trip. fa/fb = the pulled populations of row j of S_t (this thread's pair of columns); they are
+    // dead once row j of S_{t+1} is collided, so the loads of row j+1 are issued right there, into the same
+    // registers, and fly while the second step of this trip (shared-memory pulls, ~500 instructions) is computed.
+    double fa[9], fb[9];
+    load(j0, fa, fb);
     for (int j = j0; j <= j1; j++) {
-        double fa[9], fb[9];
-#pragma unroll
-        for (int i = 0; i < 9; i++) {
-            fa[i] = ga[i];
-            fb[i] = gb[i];
-        }
-        if (j < j1) load(j + 1, ga, gb);   // prefetch the next row while this one is computed
         double sa[9], sb[9];
         {
             double rho, ux, uy, p[9], e[9];
@@ -599,6 +596,7 @@ __global__ void __launch_bounds__(T, 4) k_step2x(const __grid_constant__ StepPar
             eq_from_poly(rho, p, e);
             collide(fb, e, P.omega, sb);
         }
+        if (j < j1) load(j + 1, fa, fb);
         {
             double2 *slot = reinterpret_cast<double2 *>(ring + (size_t)(j & 3) * 6 * RS) + tid;
             slot[0 * T] = make_double2(sa[2], sb[2]);
@@ -872,6 +870,58 @@ __global__ void k_minmax(long long n, const double *rho, const double *u, long l
 }
 
 // -------------------------------------------------------------------------------------------------------
+// Self-test of the hand-expanded arithmetic of lbm_device.cuh against the compiler's own IEEE operations:
+// div_by(a, b, rcp_refined(b)) == __ddiv_rn(a, b) and sqrt_rn(a) == __dsqrt_rn(a), bit for bit (NaN == NaN),
+// over operand classes chosen to reach every branch: raw random bit patterns (NaN, infinities, subnormals), the
+// physical range (rho ~ 1, |j| < 0.2), numerators and quotients around the two range-test thresholds, signed
+// zeros, exact quotients. b == 0 is outside div_by's contract (the callers test rho != 0) and is skipped.
+// -------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z)
+{
+    z += 0x9e3779b97f4a7c15ULL;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ double bits(unsigned long long sign, unsigned long long expo, unsigned long long mant)
+{
+    return __longlong_as_double((long long)(((sign & 1) << 63) | ((expo & 0x7ff) << 52) | (mant & 0xfffffffffffffULL)));
+}
+
+__global__ void k_selftest_arith(long long n, unsigned long long seed, unsigned long long *out /* [2 counts][4 operands] */)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long h0 = mix64(seed ^ (unsigned long long)i), h1 = mix64(h0), h2 = mix64(h1), h3 = mix64(h2);
+    const double u1 = (double)(h2 >> 11) * 0x1p-53, u2 = (double)(h3 >> 11) * 0x1p-53;
+    const double phys_b = 0.5 + 1.5 * u1, phys_a = (u2 - 0.5) * 0.4;
+    double a, b;
+    switch (i & 7) {
+    case 0: a = __longlong_as_double((long long)h0); b = __longlong_as_double((long long)h1); break;
+    case 1: a = phys_a; b = phys_b; break;
+    case 2: a = bits(h0, 46 + (h0 >> 8) % 18, h1); b = (h0 & 2) ? phys_b : bits(h1 >> 60, 1023 - 40 + (h1 >> 40) % 80, h2); break;   // |a.hi| around 0x036
+    case 3: a = bits(h0, h0 >> 1, h2); b = bits(h1, h1 >> 1, h3); break;                          // any exponents: tiny / huge quotients
+    case 4: a = (h0 & 1) ? -0.0 : 0.0; b = (h0 & 2) ? __longlong_as_double((long long)h1) : ((h0 & 4) ? -phys_b : phys_b); break;
+    case 5: a = phys_a; b = __longlong_as_double((long long)h1); break;
+    case 6: a = __longlong_as_double((long long)h0); b = phys_b; break;
+    default: b = phys_b; a = b * (double)((long long)(h0 % 2001) - 1000); break;                  // (nearly) exact quotients
+    }
+    if (b != 0.0) {
+        const double mine = div_by(a, b, rcp_refined(b)), ref = __ddiv_rn(a, b);
+        const bool same = __double_as_longlong(mine) == __double_as_longlong(ref) || (mine != mine && ref != ref);
+        if (!same && atomicAdd(out + 0, 1ULL) == 0) {
+            out[2] = (unsigned long long)__double_as_longlong(a);
+            out[3] = (unsigned long long)__double_as_longlong(b);
+        }
+    }
+    {
+        const double mine = sqrt_rn(a), ref = __dsqrt_rn(a);
+        const bool same = __double_as_longlong(mine) == __double_as_longlong(ref) || (mine != mine && ref != ref);
+        if (!same && atomicAdd(out + 1, 1ULL) == 0) out[4] = (unsigned long long)__double_as_longlong(a);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------------------
 struct Peer {
@@ -934,6 +984,7 @@ struct lbm_ctx {
     std::vector<GraphEntry> graphs;
     bool use_graphs = true;
     bool use_fused = true;        // LBM_NO_FUSED=1: one step per pass only (A/B measurements)
+    int fused_seg = 64;           // output rows per block of the two-step kernel (LBM_FUSED_SEG / option "fused_seg")
     bool fused_exact = false;     // tests: an even lbm_step(n) is exactly n/2 two-step passes (no one-step tail)
     bool prev_is_tm1 = false;     // S[cur^1] holds S_{t-1} (false right after a two-step pass or a load)
     // state
@@ -951,7 +1002,7 @@ struct lbm_ctx {
 };
 
 static void drop_graphs(lbm_ctx *c);
-static const int kFusedThreads = 128, kFusedSeg = 64;   // two-steps-per-pass kernel: threads per block, output rows per block
+static const int kFusedThreads = 128;   // two-steps-per-pass kernel: threads per block
 static const long long kEdgeThreshold = 1 << 20;   // cells; LBM_BC_AUTO switches to the edge kernel above this
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -1039,6 +1090,19 @@ extern "C" int lbm_streaming(int device, int nx, int ny, const double *f, double
     k_streaming_aos<<<(unsigned)((n + 255) / 256), 256>>>(nx, ny, a.as<double>(), b.as<double>());
     CK(cudaGetLastError());
     CK(cudaMemcpy(f_out, b.p, n * 72, cudaMemcpyDeviceToHost));
+    return LBM_OK;
+}
+
+extern "C" int lbm_selftest_arith(int device, int64_t n, uint64_t seed, uint64_t out[5])
+{
+    if (n < 0 || !out) return fail(LBM_ERR_ARG, "lbm_selftest_arith: bad argument");
+    if (int rc = set_device(device)) return rc;
+    DevBuf d;
+    CK(d.alloc(5 * 8));
+    CK(cudaMemset(d.p, 0, 5 * 8));
+    if (n) k_selftest_arith<<<(unsigned)((n + 255) / 256), 256>>>(n, seed, d.as<unsigned long long>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out, d.p, 5 * 8, cudaMemcpyDeviceToHost));
     return LBM_OK;
 }
 
@@ -1326,6 +1390,7 @@ extern "C" int lbm_create(int device, int nx, int ny, int ghost_x, int ghost_y, 
     if (const char *g = getenv("LBM_GENERIC_KERNEL")) c->force_generic = atoi(g) != 0;
     if (const char *g = getenv("LBM_NO_GRAPHS")) c->use_graphs = atoi(g) == 0;
     if (const char *g = getenv("LBM_NO_FUSED")) c->use_fused = atoi(g) == 0;
+    if (const char *g = getenv("LBM_FUSED_SEG")) c->fused_seg = std::max(2, atoi(g));
     if (const char *t = getenv("LBM_HALO_TIMEOUT_S")) c->timeout_cycles = (long long)(atof(t) * 2e9);
     if (int rc = ctx_build(c, bc)) {
         std::string keep = g_err;
@@ -1356,8 +1421,11 @@ extern "C" int lbm_set_option(lbm_ctx *c, const char *name, int value)
         c->force_generic = value != 0;
     else if (n == "fused_exact")
         c->fused_exact = value != 0;
-    else
-        return fail(LBM_ERR_ARG, "lbm_set_option: unknown option '%s' (fused, graphs, generic_kernel, fused_exact)", name);
+    else if (n == "fused_seg") {
+        if (value < 2) return fail(LBM_ERR_ARG, "lbm_set_option: fused_seg must be >= 2");
+        c->fused_seg = value;
+    } else
+        return fail(LBM_ERR_ARG, "lbm_set_option: unknown option '%s' (fused, graphs, generic_kernel, fused_exact, fused_seg)", name);
     return LBM_OK;
 }
 
@@ -1588,7 +1656,7 @@ static int two_steps_bc(lbm_ctx *c, const StepParams &P0, int src, int dst)
         StepParams P = P0;
         const auto ra = c->clean[i], rb = i + 1 < c->clean.size() ? c->clean[i + 1] : std::make_pair(0, 0);
         if (probe && ((c->px >= ra.first && c->px < ra.second) || (c->px >= rb.first && c->px < rb.second))) set_probe(c, P, src, dst);
-        if (int rc = fused_launch<false>(c, P, ra.first, ra.second - ra.first, rb.first, rb.second - rb.first, kFusedSeg, c->stream)) return rc;
+        if (int rc = fused_launch<false>(c, P, ra.first, ra.second - ra.first, rb.first, rb.second - rb.first, c->fused_seg, c->stream)) return rc;
     }
     for (const auto &s : c->strips) {
         const int base = (s.a + NX - 1) % NX;
@@ -1626,7 +1694,7 @@ static int two_steps(lbm_ctx *c, int src, double omega)
     if (c->has_bc) return two_steps_bc(c, P, src, dst);
     set_probe(c, P, src, dst);
     const int g = c->gx, xlo = g, xhi = c->NX - g;
-    if (!g) return fused_launch<false>(c, P, xlo, xhi - xlo, 0, 0, kFusedSeg, c->stream);
+    if (!g) return fused_launch<false>(c, P, xlo, xhi - xlo, 0, 0, c->fused_seg, c->stream);
     // two-row slabs: the 2 + 2 edge rows (readers of the ghost rows, writers of the neighbours') first on the
     // high-priority stream with the flag handshake, the interior overlaps with their NVLink stores
     const bool remote = c->any_remote;
@@ -1643,7 +1711,7 @@ static int two_steps(lbm_ctx *c, int src, double omega)
     CK(cudaEventRecord(c->ev_edge, c->stream_edge));
     StepParams Pi = P;
     for (int s = 0; s < 9; s++) Pi.halo[s].base = nullptr;
-    if (int rc = fused_launch<false>(c, Pi, xlo + g, xhi - xlo - 2 * g, 0, 0, kFusedSeg, c->stream)) return rc;
+    if (int rc = fused_launch<false>(c, Pi, xlo + g, xhi - xlo - 2 * g, 0, 0, c->fused_seg, c->stream)) return rc;
     CK(cudaStreamWaitEvent(c->stream, c->ev_edge, 0));
     if (remote) c->halo_epoch++;
     return LBM_OK;

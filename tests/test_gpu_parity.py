@@ -61,6 +61,22 @@ def test_kernels_vs_reference_golden(P, n):
     assert_parity(u2, g[n + '_step_u'], 'step u')
 
 
+def test_hand_expanded_division_and_sqrt_equal_ieee(P):
+    """lbm_device.cuh expands u = j / rho by hand (one reciprocal for both quotients) and special-cases exact zeros:
+    every quotient and root must carry the bits of the compiler's IEEE __ddiv_rn / __dsqrt_rn, over random bit
+    patterns, the physical range, the range-test thresholds, signed zeros and exact quotients."""
+    import ctypes as C
+    import struct
+    from lattice_boltzmann_parallel_solver_b200 import _native as N
+    lib = N.load()
+    out = (C.c_uint64 * 5)()
+    for seed in (1, 20261017, 0xdeadbeefcafe):
+        N.check(lib.lbm_selftest_arith(N.device(), 1 << 27, seed, out))
+        as_f = [struct.unpack('<d', struct.pack('<Q', v))[0] for v in out[2:5]]
+        assert out[0] == 0, f'{out[0]} quotients differ from __ddiv_rn, first: {as_f[0]!r} / {as_f[1]!r} ({out[2]:#x}, {out[3]:#x})'
+        assert out[1] == 0, f'{out[1]} roots differ from __dsqrt_rn, first: sqrt({as_f[2]!r}) ({out[4]:#x})'
+
+
 def test_equilibrium_1d_inputs(P, oracle):
     """boundary_conditions.py:338 calls it with (ly,), (ly,2) and gets (1, ly, 9)."""
     L = P.lattice_boltzmann_method
