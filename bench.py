@@ -257,6 +257,8 @@ def main():
     ap.add_argument('--cpu-procs', type=int, default=0, help='processes of the CPU reference arm (default: all cores)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-ref-config', action='store_true',
+                    help="skip the reference's own 420x180 scaling_test (reported beside the headline at N=1)")
     ap.add_argument('--single-step', action='store_true', help='one time step per launch only (no temporal blocking)')
     ap.add_argument('--e2e-size', type=int, default=0, help='lattice edge of the e2e job (default: --size)')
     ap.add_argument('--workload', default='shear', choices=['shear', 'karman'],
@@ -424,18 +426,63 @@ def main():
                          f'oracle/lbm_numpy.py (numpy restatement of the reference) on {k} processes x 1 thread with '
                          f'slab decomposition + ghost-row exchange (as mpirun -N {k}); host: {host_cores()} usable '
                          f'cores, {cpu_model()}; {dt:.1f} s; one process alone: {v1:.2f} MLUPS'}
+    ref_cfg = None
+    if rank == 0 and world == 1 and not args.no_ref_config and args.workload == 'shear':
+        ref_cfg = reference_scaling_test()
     if rank == 0:
         line = {
             'metric': 'D2Q9 fp64 MLUPS', 'value': mlups, 'unit': 'MLUPS', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
             'scaling': 'strong' if args.strong else 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': dict(workload_config(args, world), **({'workload': f'von Karman rule set (inlet, outlet, plate) on {args.size}x{args.size}, bc_mode={args.bc_mode}', 'omega': float(np.reciprocal(3 * 0.04 + 0.5)), 'epsilon': None} if args.workload == 'karman' else {})), 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
-            'roofline': roofline, 'cpu_baseline': cpu,
+            'roofline': roofline, 'cpu_baseline': cpu, 'reference_scaling_test': ref_cfg,
         }
         emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def reference_scaling_test(steps=20000):
+    """The reference's OWN published benchmark, through the drop-in modules: `scaling_test` of src/experiments.py:
+    723-774 — von Karman vortex street on 420 x 180, plate 40, u_in 0.1, nu 0.04, ghost-padded local arrays,
+    `parallel_von_karman_boundary_conditions` + `communication(cartesian2d)`, `time_steps` calls of
+    `lattice_boltzmann_step`, wall clock around the loop. One rank = one GPU here; the reference's figures
+     are np.load('420_180_<ranks>.npy') / 1e7: best 75.99 MLUPS on 400 MPI ranks.
+    The fields of the last step are brought to the host INSIDE the timed region (the reference's arrays are host
+    arrays when its clock stops)."""
+    import lattice_boltzmann_parallel_solver_b200 as P
+    from lattice_boltzmann_parallel_solver_b200 import dist as ldist
+    L, BU, PU = P.lattice_boltzmann_method, P.boundary_utils, P.parallelization_utils
+    lx, ly, plate, rho_in, u_in, nu = 420, 180, 40, 1.0, 0.1, 0.04
+    omega = np.reciprocal(3 * nu + 0.5)
+    comm = ldist.WorldComm()
+    x_size, y_size = PU.get_xy_size(1)
+    cart = comm.Create_cart(dims=[x_size, y_size], periods=[True, True], reorder=False)
+    coords = cart.Get_coords(0)
+    nlx, nly = PU.get_local_coords(coords, lx, ly, x_size, y_size)
+    density = np.ones((nlx + 2, nly + 2))
+    velocity = np.zeros((nlx + 2, nly + 2, 2))
+    velocity[..., 0] = u_in                                  # density_1_velocity_x_u0_velocity_y_0_initial
+    f = L.equilibrium_distr_func(density, velocity)
+    bound = BU.parallel_von_karman_boundary_conditions(coords, nlx, nly, lx, ly, x_size, y_size, rho_in, u_in, plate)
+    com = PU.communication(cart)
+    out = {}
+    for label, n in (('warmup', 2000), ('timed', steps)):
+        fi, di, vi = f, density, velocity
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fi, di, vi = L.lattice_boltzmann_step(fi, di, vi, omega, bound, com)
+        vmax = float(np.max(np.abs(np.asarray(vi))))
+        out[label] = time.perf_counter() - t0
+    L.release_lattices()
+    mlups = lx * ly * steps / out['timed'] / 1e6
+    return {'workload': 'scaling_test of src/experiments.py:723-774: von Karman 420x180, plate 40, 1 rank = 1 GPU, '
+                        'driven through the drop-in lattice_boltzmann_step / boundary_utils / parallelization_utils',
+            'steps': steps, 'seconds': out['timed'], 'us_per_step': 1e6 * out['timed'] / steps, 'mlups': mlups,
+            'max_abs_velocity': vmax,
+            'published_best_mlups': 75.99, 'published_best_ranks': 400, 'ratio_vs_published_best': mlups / 75.99,
+            'published_source': 'figures/von_karman_vortex_shedding/scaling_test/420_180_400.npy (BASELINE.md section 1)'}
 
 
 def karman_lattice(nx, ny, bc_mode):

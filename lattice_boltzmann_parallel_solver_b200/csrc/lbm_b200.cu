@@ -142,22 +142,29 @@ __device__ __forceinline__ void snapshot_ghosts(const StepParams &P, int x, int 
     const bool xl = P.gx && x == P.gx, xh = P.gx && x == P.NX - 1 - P.gx;
     const bool yl = P.gy && y == P.gy, yh = P.gy && y == P.NY - 1 - P.gy;
     if (!(xl | xh | yl | yh)) return;
+    // All loads of a copy are issued before its first store: the compiler cannot prove that the snapshot does not
+    // alias S, and a load-store-load-store chain costs nine L2 round trips per copy (this was most of a
+    // launch-bound von Karman step, profiles/r01_summary.md section 9).
+    auto copy9 = [&](const double *src, long long sstride, double *dst, long long dstride) {
+        double v[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) v[i] = ldS(src + i * sstride);
+#pragma unroll
+        for (int i = 0; i < 9; i++) dst[i * dstride] = v[i];
+    };
 #pragma unroll 1
     for (int side = 0; side < 2; side++) {
         if (side ? xh : xl) {
             const int gx_row = side ? P.NX - P.gx : P.gx - 1;
             const double *src = P.src + (long long)gx_row * P.pitch;
             double *dst = P.snap_row + (long long)side * 9 * P.pitch;
-            for (int i = 0; i < 9; i++) {
-                dst[i * (long long)P.pitch + y] = ldS(src + i * P.plane + y);
-                if (yl) dst[i * (long long)P.pitch] = ldS(src + i * P.plane);
-                if (yh) dst[i * (long long)P.pitch + P.NY - 1] = ldS(src + i * P.plane + P.NY - 1);
-            }
+            copy9(src + y, P.plane, dst + y, P.pitch);
+            if (yl) copy9(src, P.plane, dst, P.pitch);
+            if (yh) copy9(src + P.NY - 1, P.plane, dst + P.NY - 1, P.pitch);
         }
         if (side ? yh : yl) {
             const int gy_col = side ? P.NY - 1 : 0;
-            double *dst = P.snap_col + (long long)side * 9 * P.NX;
-            for (int i = 0; i < 9; i++) dst[i * (long long)P.NX + x] = ldS(P.src + i * P.plane + (long long)x * P.pitch + gy_col);
+            copy9(P.src + (long long)x * P.pitch + gy_col, P.plane, P.snap_col + (long long)side * 9 * P.NX + x, P.NX);
         }
     }
 }
@@ -984,7 +991,7 @@ struct lbm_ctx {
     std::vector<GraphEntry> graphs;
     bool use_graphs = true;
     bool use_fused = true;        // LBM_NO_FUSED=1: one step per pass only (A/B measurements)
-    int fused_seg = 64;           // output rows per block of the two-step kernel (LBM_FUSED_SEG / option "fused_seg")
+    int fused_seg = 0;            // output rows per block of the two-step kernel; 0 = pick_seg (LBM_FUSED_SEG / option "fused_seg")
     bool fused_exact = false;     // tests: an even lbm_step(n) is exactly n/2 two-step passes (no one-step tail)
     bool prev_is_tm1 = false;     // S[cur^1] holds S_{t-1} (false right after a two-step pass or a load)
     // state
@@ -1360,7 +1367,9 @@ static int ctx_build(lbm_ctx *c, const lbm_bc_desc *bc)
         if (c->n_cells) {
             CK(cudaMalloc(&c->cells, cells.size() * sizeof(int2)));
             CK(cudaMemcpyAsync(c->cells, cells.data(), cells.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
-            if (!any_pbc && !c->gx && !c->gy)
+            // (same size conditions as fused_ok: small lattices never take the two-step pass)
+            if (!any_pbc && !c->gx && !c->gy && c->NY >= 2 * kFusedThreads && (c->NY % 2) == 0 &&
+                (long long)c->NX * c->NY >= kEdgeThreshold)
                 if (int rc = plan_strips(c, cells)) return rc;
         } else {
             c->has_bc = false;
@@ -1390,7 +1399,7 @@ extern "C" int lbm_create(int device, int nx, int ny, int ghost_x, int ghost_y, 
     if (const char *g = getenv("LBM_GENERIC_KERNEL")) c->force_generic = atoi(g) != 0;
     if (const char *g = getenv("LBM_NO_GRAPHS")) c->use_graphs = atoi(g) == 0;
     if (const char *g = getenv("LBM_NO_FUSED")) c->use_fused = atoi(g) == 0;
-    if (const char *g = getenv("LBM_FUSED_SEG")) c->fused_seg = std::max(2, atoi(g));
+    if (const char *g = getenv("LBM_FUSED_SEG")) c->fused_seg = atoi(g) >= 2 ? atoi(g) : 0;
     if (const char *t = getenv("LBM_HALO_TIMEOUT_S")) c->timeout_cycles = (long long)(atof(t) * 2e9);
     if (int rc = ctx_build(c, bc)) {
         std::string keep = g_err;
@@ -1422,7 +1431,7 @@ extern "C" int lbm_set_option(lbm_ctx *c, const char *name, int value)
     else if (n == "fused_exact")
         c->fused_exact = value != 0;
     else if (n == "fused_seg") {
-        if (value < 2) return fail(LBM_ERR_ARG, "lbm_set_option: fused_seg must be >= 2");
+        if (value < 2 && value != 0) return fail(LBM_ERR_ARG, "lbm_set_option: fused_seg must be >= 2, or 0 for the default");
         c->fused_seg = value;
     } else
         return fail(LBM_ERR_ARG, "lbm_set_option: unknown option '%s' (fused, graphs, generic_kernel, fused_exact, fused_seg)", name);
@@ -1621,6 +1630,20 @@ static bool fused_ok(const lbm_ctx *c)
            (c->NX - 2 * c->gx) >= 8 && (long long)c->NX * c->NY >= kEdgeThreshold && (!c->gx || c->halo_ready);
 }
 
+// Output rows per thread block of the two-step kernel. Every block recomputes one intermediate row at each end of
+// its segment (2 / seg redundant work), but a lattice of a few million cells needs short segments to fill the
+// 148 SMs x 4 resident blocks several times over. Measured (tools/fused_sweep.py, profiles/r01c_fused_sweep.txt):
+// the best segment is the longest one that still gives ~2000 blocks — 8 rows at 1536^2, 16 at 3072^2, 32 at 4096^2,
+// 64 from 8192^2 on.
+static int pick_seg(const lbm_ctx *c, int rows)
+{
+    if (c->fused_seg) return c->fused_seg;
+    const long long strips = (c->NY + 2 * kFusedThreads - 5) / (2 * kFusedThreads - 4);
+    int seg = 64;
+    while (seg > 8 && strips * ((rows + seg - 1) / seg) < 2000) seg /= 2;
+    return seg;
+}
+
 template <bool HALO>
 static int fused_launch(lbm_ctx *c, StepParams P, int row0a, int na, int row0b, int nb, int seg, cudaStream_t st)
 {
@@ -1656,7 +1679,7 @@ static int two_steps_bc(lbm_ctx *c, const StepParams &P0, int src, int dst)
         StepParams P = P0;
         const auto ra = c->clean[i], rb = i + 1 < c->clean.size() ? c->clean[i + 1] : std::make_pair(0, 0);
         if (probe && ((c->px >= ra.first && c->px < ra.second) || (c->px >= rb.first && c->px < rb.second))) set_probe(c, P, src, dst);
-        if (int rc = fused_launch<false>(c, P, ra.first, ra.second - ra.first, rb.first, rb.second - rb.first, c->fused_seg, c->stream)) return rc;
+        if (int rc = fused_launch<false>(c, P, ra.first, ra.second - ra.first, rb.first, rb.second - rb.first, pick_seg(c, c->NX), c->stream)) return rc;
     }
     for (const auto &s : c->strips) {
         const int base = (s.a + NX - 1) % NX;
@@ -1694,7 +1717,7 @@ static int two_steps(lbm_ctx *c, int src, double omega)
     if (c->has_bc) return two_steps_bc(c, P, src, dst);
     set_probe(c, P, src, dst);
     const int g = c->gx, xlo = g, xhi = c->NX - g;
-    if (!g) return fused_launch<false>(c, P, xlo, xhi - xlo, 0, 0, c->fused_seg, c->stream);
+    if (!g) return fused_launch<false>(c, P, xlo, xhi - xlo, 0, 0, pick_seg(c, xhi - xlo), c->stream);
     // two-row slabs: the 2 + 2 edge rows (readers of the ghost rows, writers of the neighbours') first on the
     // high-priority stream with the flag handshake, the interior overlaps with their NVLink stores
     const bool remote = c->any_remote;
@@ -1711,7 +1734,7 @@ static int two_steps(lbm_ctx *c, int src, double omega)
     CK(cudaEventRecord(c->ev_edge, c->stream_edge));
     StepParams Pi = P;
     for (int s = 0; s < 9; s++) Pi.halo[s].base = nullptr;
-    if (int rc = fused_launch<false>(c, Pi, xlo + g, xhi - xlo - 2 * g, 0, 0, c->fused_seg, c->stream)) return rc;
+    if (int rc = fused_launch<false>(c, Pi, xlo + g, xhi - xlo - 2 * g, 0, 0, pick_seg(c, xhi - xlo - 2 * g), c->stream)) return rc;
     CK(cudaStreamWaitEvent(c->stream, c->ev_edge, 0));
     if (remote) c->halo_epoch++;
     return LBM_OK;

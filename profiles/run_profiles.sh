@@ -5,7 +5,7 @@ set -u
 TAG=${1:-r01}
 OUT=gpurun_out
 mkdir -p $OUT
-BENCH="python bench.py --steps 7 --warmup 3 --no-e2e --no-cpu"
+BENCH="python bench.py --steps 7 --warmup 3 --no-e2e --no-cpu --no-ref-config"
 # 1. launch list of the bench command (cold-cache, serialised: compare SHARES)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches_${TAG}.csv $BENCH > $OUT/launches_${TAG}.log 2>&1
 # 2. full capture of the dominant kernel (two steps per launch) and of the one-step kernel

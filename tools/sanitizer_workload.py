@@ -26,6 +26,17 @@ print('two-row slab (self neighbour) ran')
 blk[(0, 0)].close()
 import lattice_boltzmann_parallel_solver_b200 as P
 from lattice_boltzmann_parallel_solver_b200 import _native as N
+# two steps per pass on a lattice WITH boundary cells: k_step2x on the clean rows, mask launches through strip windows
+shape = (4096, 256)
+B, BU = P.boundary_conditions, P.boundary_utils
+plate = np.zeros(shape, dtype=bool); plate[1024, 100:156] = True
+bundle = BU.BoundaryBundle('von_karman_serial', shape)
+bundle.add(B.inlet(shape, 1.0, 0.1)).add(B.outlet()).add(B.rigid_object(plate))
+rho = rng.uniform(0.9, 1.1, shape); u = rng.uniform(-0.05, 0.05, shape + (2,)); f = onp.equilibrium(rho, u)
+lat = Lattice(*shape, bundle.kind_map(shape)); lat.probe(4094, 3, 16); lat.load(f, rho, u, 1.3); l0 = lat.launches; lat.run(5)
+ref = oc.run(f, rho, u, 1.3, oc.karman(4096, 256, 1.0, 0.1, 56, ghost=0), 5)
+print('fused with boundary strips ok', lat.launches - l0 == 2 * 5 + 2, all(np.array_equal(a, b) for a, b in zip(lat.fields(), ref)))
+lat.close()
 for mode in (N.BC_MASK, N.BC_EDGE):
     lx, ly = 62, 40
     bc = P.boundary_utils.parallel_von_karman_boundary_conditions([0, 0], lx, ly, lx, ly, 1, 1, 1.0, 0.1, 8)
