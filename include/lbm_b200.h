@@ -129,6 +129,8 @@ int lbm_set_bc_mode(lbm_ctx *ctx, int mode);
  *   "generic_kernel" force the one-cell-per-thread step kernel
  *   "fused_exact"    (default 0) an even lbm_step(n) is exactly n/2 two-step passes without the one-step tail that
  *                    normally ends every call; results cannot be materialised until one more single step is taken
+ *   "l2_prefetch"    (default 2) rows ahead of its march whose source segments the two-step kernel prefetches into
+ *                    L2 with cp.async.bulk.prefetch; 0 = off
  *   "fused_seg"      output rows per thread block of the two-step kernel (default 0: 8..64 by lattice size)
  * Environment overrides at lbm_create: LBM_NO_FUSED=1, LBM_NO_GRAPHS=1, LBM_GENERIC_KERNEL=1, LBM_FUSED_SEG=n. */
 int lbm_set_option(lbm_ctx *ctx, const char *name, int value);

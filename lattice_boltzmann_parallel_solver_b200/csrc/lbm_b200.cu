@@ -78,6 +78,7 @@ struct StepParams {
     int row0a, na, row0b;
     int bpr;           // blocks per row
     int seg, nb;       // k_step2x: output rows per block; length of the second row range
+    int pf;            // k_step2x: rows ahead of the march whose source segments are prefetched into L2 (0 = off)
     int y0, y1;        // columns handled: [y0, y1)
     double omega;
     const uint8_t *kind_map;   // [x*pitch + y] or null
@@ -580,6 +581,19 @@ __global__ void __launch_bounds__(T, 4) k_step2x(const __grid_constant__ StepPar
     double fa[9], fb[9];
     load(j0, fa, fb);
     for (int j = j0; j <= j1; j++) {
+        // L2 prefetch of the nine 2 KB source segments of row j + pf (cp.async.bulk.prefetch: no registers, no
+        // shared memory, one thread per block). The real loads, issued half a trip ahead, then hit L2.
+        if (tid == 0 && P.pf && j + P.pf <= j1) {
+            const int jj = j + P.pf, c0 = max(y0 - 4, 0);
+            const unsigned bytes = (unsigned)(min(y0 + 2 * T, P.pitch) - c0) * 8u;
+            const double *r0 = P.src + (long long)wrapx(jj) * P.pitch + c0, *rm = P.src + (long long)wrapx(jj - 1) * P.pitch + c0,
+                         *rp = P.src + (long long)wrapx(jj + 1) * P.pitch + c0;
+            constexpr int cx[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1};
+#pragma unroll
+            for (int i = 0; i < 9; i++)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((cx[i] == 1 ? rm : (cx[i] == -1 ? rp : r0)) + i * pl), "r"(bytes)
+                             : "memory");
+        }
         double sa[9], sb[9];
         {
             double rho, ux, uy, p[9], e[9];
@@ -991,6 +1005,7 @@ struct lbm_ctx {
     std::vector<GraphEntry> graphs;
     bool use_graphs = true;
     bool use_fused = true;        // LBM_NO_FUSED=1: one step per pass only (A/B measurements)
+    int l2_prefetch = 2;          // rows ahead whose source segments k_step2x prefetches into L2 (option "l2_prefetch")
     int fused_seg = 0;            // output rows per block of the two-step kernel; 0 = pick_seg (LBM_FUSED_SEG / option "fused_seg")
     bool fused_exact = false;     // tests: an even lbm_step(n) is exactly n/2 two-step passes (no one-step tail)
     bool prev_is_tm1 = false;     // S[cur^1] holds S_{t-1} (false right after a two-step pass or a load)
@@ -1430,11 +1445,14 @@ extern "C" int lbm_set_option(lbm_ctx *c, const char *name, int value)
         c->force_generic = value != 0;
     else if (n == "fused_exact")
         c->fused_exact = value != 0;
-    else if (n == "fused_seg") {
+    else if (n == "l2_prefetch") {
+        if (value < 0 || value > 8) return fail(LBM_ERR_ARG, "lbm_set_option: l2_prefetch must be 0..8 rows");
+        c->l2_prefetch = value;
+    } else if (n == "fused_seg") {
         if (value < 2 && value != 0) return fail(LBM_ERR_ARG, "lbm_set_option: fused_seg must be >= 2, or 0 for the default");
         c->fused_seg = value;
     } else
-        return fail(LBM_ERR_ARG, "lbm_set_option: unknown option '%s' (fused, graphs, generic_kernel, fused_exact, fused_seg)", name);
+        return fail(LBM_ERR_ARG, "lbm_set_option: unknown option '%s' (fused, graphs, generic_kernel, fused_exact, fused_seg, l2_prefetch)", name);
     return LBM_OK;
 }
 
@@ -1657,6 +1675,7 @@ static int fused_launch(lbm_ctx *c, StepParams P, int row0a, int na, int row0b, 
     P.row0b = row0b;
     P.nb = nb;
     P.seg = seg;
+    P.pf = c->l2_prefetch;
     dim3 grid((c->NY + 2 * T - 5) / (2 * T - 4), (na + seg - 1) / seg + (nb + seg - 1) / seg);
     P.n_blocks = (int)(grid.x * grid.y);
     if (P.probe)
