@@ -571,117 +571,126 @@ __global__ void __launch_bounds__(T, 4) k_step2x(const __grid_constant__ StepPar
         ga[8] = ldS(rm + 8 * pl + ca + 1); gb[8] = ldS(rm + 8 * pl + cq);
     };
     const long long tc = PROBE ? *P.tc_in : 0;
-    // register pass-through of the unshifted populations of S_{t+1}: pop 0 of row j-1, pop 1 of rows j-1 and j-2
-    double a0p = 0, b0p = 0, a1p = 0, b1p = 0, a1pp = 0, b1pp = 0;
     const int j0 = x0 - 1, j1 = x1;     // intermediate rows j0..j1 inclusive
 
-    // One row per trip. fa/fb = the pulled populations of row j of S_t (this thread's pair of columns); they are
-    // dead once row j of S_{t+1} is collided, so the loads of row j+1 are issued right there, into the same
-    // registers, and fly while the second step of this trip (shared-memory pulls, ~500 instructions) is computed.
-    double fa[9], fb[9];
-    load(j0, fa, fb);
-    for (int j = j0; j <= j1; j++) {
-        // L2 prefetch of the nine 2 KB source segments of row j + pf (cp.async.bulk.prefetch: no registers, no
-        // shared memory, one thread per block). The real loads, issued half a trip ahead, then hit L2.
-        if (tid == 0 && P.pf && j + P.pf <= j1) {
-            const int jj = j + P.pf, c0 = max(y0 - 4, 0);
-            const unsigned bytes = (unsigned)(min(y0 + 2 * T, P.pitch) - c0) * 8u;
-            const double *r0 = P.src + (long long)wrapx(jj) * P.pitch + c0, *rm = P.src + (long long)wrapx(jj - 1) * P.pitch + c0,
-                         *rp = P.src + (long long)wrapx(jj + 1) * P.pitch + c0;
-            constexpr int cx[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1};
+    // L2 prefetch of the nine 2 KB source segments of row jj (cp.async.bulk.prefetch: no registers, no shared
+    // memory, one thread per block); the real loads then hit L2.
+    auto prefetch_row = [&](int jj) {
+        const int c0 = max(y0 - 4, 0);
+        const unsigned bytes = (unsigned)(min(y0 + 2 * T, P.pitch) - c0) * 8u;
+        const double *r0 = P.src + (long long)wrapx(jj) * P.pitch + c0, *rm = P.src + (long long)wrapx(jj - 1) * P.pitch + c0,
+                     *rp = P.src + (long long)wrapx(jj + 1) * P.pitch + c0;
+        constexpr int cx[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1};
 #pragma unroll
-            for (int i = 0; i < 9; i++)
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((cx[i] == 1 ? rm : (cx[i] == -1 ? rp : r0)) + i * pl), "r"(bytes)
-                             : "memory");
+        for (int i = 0; i < 9; i++)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((cx[i] == 1 ? rm : (cx[i] == -1 ? rp : r0)) + i * pl), "r"(bytes)
+                         : "memory");
+    };
+    // first step: row j of S_{t+1} (this thread's pair of columns) from the pulled populations fa / fb
+    auto first_step = [&](int j, const double (&fa)[9], const double (&fb)[9], double (&sa)[9], double (&sb)[9]) {
+        double rho, ux, uy, p[9], e[9];
+        const bool probe_row = PROBE && wrapx(j) == P.px;
+        moments(fa, rho, ux, uy);
+        if (probe_row && ca == P.py) {   // time t+1 (redundant rows/columns write identical values)
+            double *slot = P.probe + 2 * ((tc + 1) % P.probe_cap);
+            slot[0] = ux;
+            slot[1] = uy;
         }
-        double sa[9], sb[9];
+        eq_poly(ux, uy, p);
+        eq_from_poly(rho, p, e);
+        collide(fa, e, P.omega, sa);
+        moments(fb, rho, ux, uy);
+        if (probe_row && ca + 1 == P.py) {
+            double *slot = P.probe + 2 * ((tc + 1) % P.probe_cap);
+            slot[0] = ux;
+            slot[1] = uy;
+        }
+        eq_poly(ux, uy, p);
+        eq_from_poly(rho, p, e);
+        collide(fb, e, P.omega, sb);
+    };
+    auto ring_store = [&](int j, const double (&sa)[9], const double (&sb)[9]) {
+        double2 *slot = reinterpret_cast<double2 *>(ring + (size_t)(j & 3) * 6 * RS) + tid;
+        slot[0 * T] = make_double2(sa[2], sb[2]);
+        slot[1 * T] = make_double2(sa[4], sb[4]);
+        slot[2 * T] = make_double2(sa[5], sb[5]);
+        slot[3 * T] = make_double2(sa[6], sb[6]);
+        slot[4 * T] = make_double2(sa[7], sb[7]);
+        slot[5 * T] = make_double2(sa[8], sb[8]);
+    };
+    // second step: row r of S_{t+2} from intermediate rows r-1 (A), r (B), r+1 (D) in the ring and the unshifted
+    // populations handed over in registers (0 of row r, 1 of row r-1, 3 of row r+1)
+    auto second_step = [&](int r, double h0a, double h0b, double h1a, double h1b, double h3a, double h3b) {
+        const double *A = ring + (size_t)((r - 1) & 3) * 6 * RS + 2 * tid;
+        const double *B = ring + (size_t)(r & 3) * 6 * RS + 2 * tid;
+        const double *D = ring + (size_t)((r + 1) & 3) * 6 * RS + 2 * tid;
+        double ha[9], hb[9];
+        ha[0] = h0a;           hb[0] = h0b;
+        ha[1] = h1a;           hb[1] = h1b;
+        ha[3] = h3a;           hb[3] = h3b;
+        ha[2] = B[0 * RS - 1]; hb[2] = B[0 * RS];
+        ha[4] = B[1 * RS + 1]; hb[4] = B[1 * RS + 2];
+        ha[5] = A[2 * RS - 1]; hb[5] = A[2 * RS];
+        ha[6] = D[3 * RS - 1]; hb[6] = D[3 * RS];
+        ha[7] = D[4 * RS + 1]; hb[7] = D[4 * RS + 2];
+        ha[8] = A[5 * RS + 1]; hb[8] = A[5 * RS + 2];
+        const int xo = wrapx(r);
+        const bool probe_row = PROBE && xo == P.px;
+        double ta[9], tb[9];
         {
             double rho, ux, uy, p[9], e[9];
-            const bool probe_row = PROBE && wrapx(j) == P.px;
-            moments(fa, rho, ux, uy);
-            if (probe_row && ca == P.py) {   // time t+1 (redundant rows/columns write identical values)
-                double *slot = P.probe + 2 * ((tc + 1) % P.probe_cap);
+            moments(ha, rho, ux, uy);
+            if (probe_row && yo == P.py) {        // time t+2: also advances the device clock
+                double *slot = P.probe + 2 * ((tc + 2) % P.probe_cap);
                 slot[0] = ux;
                 slot[1] = uy;
+                *P.tc_out = tc + 2;
             }
             eq_poly(ux, uy, p);
             eq_from_poly(rho, p, e);
-            collide(fa, e, P.omega, sa);
-            moments(fb, rho, ux, uy);
-            if (probe_row && ca + 1 == P.py) {
-                double *slot = P.probe + 2 * ((tc + 1) % P.probe_cap);
+            collide(ha, e, P.omega, ta);
+            moments(hb, rho, ux, uy);
+            if (probe_row && yo + 1 == P.py) {
+                double *slot = P.probe + 2 * ((tc + 2) % P.probe_cap);
                 slot[0] = ux;
                 slot[1] = uy;
+                *P.tc_out = tc + 2;
             }
             eq_poly(ux, uy, p);
             eq_from_poly(rho, p, e);
-            collide(fb, e, P.omega, sb);
+            collide(hb, e, P.omega, tb);
         }
-        if (j < j1) load(j + 1, fa, fb);
-        {
-            double2 *slot = reinterpret_cast<double2 *>(ring + (size_t)(j & 3) * 6 * RS) + tid;
-            slot[0 * T] = make_double2(sa[2], sb[2]);
-            slot[1 * T] = make_double2(sa[4], sb[4]);
-            slot[2 * T] = make_double2(sa[5], sb[5]);
-            slot[3 * T] = make_double2(sa[6], sb[6]);
-            slot[4 * T] = make_double2(sa[7], sb[7]);
-            slot[5 * T] = make_double2(sa[8], sb[8]);
-        }
-        __syncthreads();
-        if (j >= x0 + 1 && out_pair) {   // second step: row j-1 of S_{t+2} from intermediate rows j-2 (A), j-1 (B), j (D)
-            const double *A = ring + (size_t)((j - 2) & 3) * 6 * RS + 2 * tid;
-            const double *B = ring + (size_t)((j - 1) & 3) * 6 * RS + 2 * tid;
-            const double *D = ring + (size_t)(j & 3) * 6 * RS + 2 * tid;
-            double ha[9], hb[9];
-            ha[0] = a0p;           hb[0] = b0p;
-            ha[1] = a1pp;          hb[1] = b1pp;
-            ha[3] = sa[3];         hb[3] = sb[3];
-            ha[2] = B[0 * RS - 1]; hb[2] = B[0 * RS];
-            ha[4] = B[1 * RS + 1]; hb[4] = B[1 * RS + 2];
-            ha[5] = A[2 * RS - 1]; hb[5] = A[2 * RS];
-            ha[6] = D[3 * RS - 1]; hb[6] = D[3 * RS];
-            ha[7] = D[4 * RS + 1]; hb[7] = D[4 * RS + 2];
-            ha[8] = A[5 * RS + 1]; hb[8] = A[5 * RS + 2];
-            const int xo = wrapx(j - 1);
-            const bool probe_row = PROBE && xo == P.px;
-            double ta[9], tb[9];
-            {
-                double rho, ux, uy, p[9], e[9];
-                moments(ha, rho, ux, uy);
-                if (probe_row && yo == P.py) {        // time t+2: also advances the device clock
-                    double *slot = P.probe + 2 * ((tc + 2) % P.probe_cap);
-                    slot[0] = ux;
-                    slot[1] = uy;
-                    *P.tc_out = tc + 2;
-                }
-                eq_poly(ux, uy, p);
-                eq_from_poly(rho, p, e);
-                collide(ha, e, P.omega, ta);
-                moments(hb, rho, ux, uy);
-                if (probe_row && yo + 1 == P.py) {
-                    double *slot = P.probe + 2 * ((tc + 2) % P.probe_cap);
-                    slot[0] = ux;
-                    slot[1] = uy;
-                    *P.tc_out = tc + 2;
-                }
-                eq_poly(ux, uy, p);
-                eq_from_poly(rho, p, e);
-                collide(hb, e, P.omega, tb);
-            }
-            double *o = P.dst + (long long)xo * P.pitch + yo;
+        double *o = P.dst + (long long)xo * P.pitch + yo;
 #pragma unroll
-            for (int i = 0; i < 9; i++) st2(o + i * pl, ta[i], tb[i]);
-            if (HALO) {   // no ghost snapshot: nothing is materialised from a two-step pass
-                store_halo(P, xo, yo, ta);
-                store_halo(P, xo, yo + 1, tb);
-            }
+        for (int i = 0; i < 9; i++) st2(o + i * pl, ta[i], tb[i]);
+        if (HALO) {   // no ghost snapshot: nothing is materialised from a two-step pass
+            store_halo(P, xo, yo, ta);
+            store_halo(P, xo, yo + 1, tb);
         }
-        a1pp = a1p;
-        b1pp = b1p;
-        a1p = sa[1];
-        b1p = sb[1];
-        a0p = sa[0];
-        b0p = sb[0];
+    };
+
+    double fa[9], fb[9];
+    {
+        // One row per trip: first step of row j -> ring -> barrier -> second step of row j-1. fa/fb are dead once
+        // row j is collided, so the loads of row j+1 are issued right there, into the same registers, and fly while
+        // the second step is computed. Unshifted populations in registers: 0 of row j-1, 1 of rows j-1 and j-2.
+        double a0p = 0, b0p = 0, a1p = 0, b1p = 0, a1pp = 0, b1pp = 0;
+        load(j0, fa, fb);
+        for (int j = j0; j <= j1; j++) {
+            if (tid == 0 && P.pf && j + P.pf <= j1) prefetch_row(j + P.pf);
+            double sa[9], sb[9];
+            first_step(j, fa, fb, sa, sb);
+            if (j < j1) load(j + 1, fa, fb);
+            ring_store(j, sa, sb);
+            __syncthreads();
+            if (j >= x0 + 1 && out_pair) second_step(j - 1, a0p, b0p, a1pp, b1pp, sa[3], sb[3]);
+            a1pp = a1p;
+            b1pp = b1p;
+            a1p = sa[1];
+            b1p = sb[1];
+            a0p = sa[0];
+            b0p = sb[0];
+        }
     }
     if (HALO) halo_signal(P);
 }
