@@ -125,17 +125,14 @@ int lbm_set_bc_mode(lbm_ctx *ctx, int mode);
  *                    boundary cells the rows whose two-step dependency cone is all fluid take the two-step kernel,
  *                    the other rows two one-step mask launches through a strip window (needs ghost_x = ghost_y = 0,
  *                    no pressure-periodic rows, and boundary cells on at most half of the rows)
- *   "persistent"     many time steps per cooperative launch on launch-bound lattices (< 2^20 cells, no remote halo
- *                    neighbours): resident blocks, one grid barrier per step
- *   "graphs"         CUDA-graph replay of 32 captured steps on launch-bound lattices (when "persistent" is off or
- *                    cooperative launches are unavailable)
+ *   "graphs"         CUDA-graph replay of 32 captured steps on launch-bound lattices
  *   "generic_kernel" force the one-cell-per-thread step kernel
  *   "fused_exact"    (default 0) an even lbm_step(n) is exactly n/2 two-step passes without the one-step tail that
  *                    normally ends every call; results cannot be materialised until one more single step is taken
  *   "l2_prefetch"    (default 2) rows ahead of its march whose source segments the two-step kernel prefetches into
  *                    L2 with cp.async.bulk.prefetch; 0 = off
  *   "fused_seg"      output rows per thread block of the two-step kernel (default 0: 8..64 by lattice size)
- * Environment overrides at lbm_create: LBM_NO_FUSED=1, LBM_NO_PERSISTENT=1, LBM_NO_GRAPHS=1, LBM_GENERIC_KERNEL=1, LBM_FUSED_SEG=n. */
+ * Environment overrides at lbm_create: LBM_NO_FUSED=1, LBM_NO_GRAPHS=1, LBM_GENERIC_KERNEL=1, LBM_FUSED_SEG=n. */
 int lbm_set_option(lbm_ctx *ctx, const char *name, int value);
 /* bytes of device memory the context holds */
 int64_t lbm_device_bytes(const lbm_ctx *ctx);

@@ -451,57 +451,6 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepParams
 }
 
 // -------------------------------------------------------------------------------------------------------
-// Launch-bound lattices (configs 1-4 of BASELINE.json, <= 77 k cells, resident in L2): MANY time steps in ONE
-// cooperative launch. A 420 x 180 step is ~1 us of work behind ~4 us of per-launch fixed cost (launch gap, cold
-// constant and instruction caches, first-touch latencies; profiles/r01_summary.md section 12); here the blocks stay
-// resident, march over the steps with the A/B parameter blocks alternating, and meet at a grid barrier (one atomic
-// counter + a generation word, bounded spin) after every step. Cross-step data goes through L2 only: S, the outlet
-// side buffers and the probe clock are read with ld.global.cg, written with plain / .cg stores followed by
-// __threadfence. Same per-cell code as k_step (step_cell), hence the same bits.
-// -------------------------------------------------------------------------------------------------------
-struct MultiParams {
-    StepParams P[2];          // P[0]: S[cur] -> S[cur^1], P[1]: the way back
-    int n_steps, n_rows;      // rows [P.row0a, P.row0a + n_rows), columns [P.y0, P.y1)
-    unsigned *bar_count;      // arrivals of the current barrier
-    unsigned *bar_gen;        // number of barriers completed since the context was built
-    unsigned gen0;            // its value when this launch starts
-};
-
-__device__ __forceinline__ void grid_barrier(const MultiParams &M, unsigned target)
-{
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(M.bar_count, 1u) == gridDim.x - 1) {
-            atomicExch(M.bar_count, 0u);
-            __threadfence();
-            atomicExch(M.bar_gen, target);
-        } else {
-            const long long t0 = clock64();
-            while ((int)(*(volatile unsigned *)M.bar_gen - target) < 0) {
-                if (clock64() - t0 > M.P[0].timeout_cycles) {   // cannot happen with a cooperative launch; never hang the device
-                    atomicExch(M.P[0].err_flag, 0xC0000000u);
-                    break;
-                }
-            }
-        }
-        __threadfence();
-    }
-    __syncthreads();
-}
-
-template <bool MASK, bool HALO>
-__global__ void __launch_bounds__(256) k_multi(const __grid_constant__ MultiParams M)
-{
-    for (int s = 0; s < M.n_steps; s++) {
-        const StepParams &P = M.P[s & 1];
-        for (int r = blockIdx.x; r < M.n_rows; r += gridDim.x)
-            for (int y = P.y0 + threadIdx.x; y < P.y1; y += blockDim.x) step_cell<MASK, HALO, false>(P, P.row0a + r, y);
-        if (s + 1 < M.n_steps) grid_barrier(M, M.gen0 + s + 1);
-    }
-}
-
-// -------------------------------------------------------------------------------------------------------
 // The bandwidth kernel: fluid cells only (no kind byte, no ghost stores), TWO cells per thread along the fast axis.
 //  * blockIdx.y is the row (no integer division), the three row bases are computed once per thread;
 //  * the three populations that do not move along y (0, 1, 3) are read with 128-bit loads, the six shifted ones
@@ -1069,10 +1018,6 @@ struct lbm_ctx {
     };
     std::vector<GraphEntry> graphs;
     bool use_graphs = true;
-    bool use_persistent = true;   // many steps per cooperative launch on launch-bound lattices (LBM_NO_PERSISTENT=1 / option "persistent")
-    int coop_blocks[4] = {0, 0, 0, 0};   // co-resident blocks of k_multi<MASK,HALO> at 256 threads (0 = not queried, -1 = unsupported)
-    unsigned *bar = nullptr;      // device [2]: arrivals, generation
-    unsigned bar_gen = 0;         // host copy of the generation
     bool use_fused = true;        // LBM_NO_FUSED=1: one step per pass only (A/B measurements)
     int l2_prefetch = 2;          // rows ahead whose source segments k_step2x prefetches into L2 (option "l2_prefetch")
     int fused_seg = 0;            // output rows per block of the two-step kernel; 0 = pick_seg (LBM_FUSED_SEG / option "fused_seg")
@@ -1290,7 +1235,7 @@ extern "C" int lbm_destroy(lbm_ctx *c)
     for (auto &s : c->strips)
         if (s.buf) cudaFree(s.buf);
     void *bufs[] = {c->arena,  c->kind_map, c->kinds,    c->ktab,   c->ctab,  c->outbuf[0],   c->outbuf[1], c->outbuf[2], c->cells, c->snap_row, c->snap_col,
-                    c->done_counter, c->err_flag, c->bar, c->stage_f, c->stage_rho, c->stage_u, c->mm_acc, c->probe, c->tcount};
+                    c->done_counter, c->err_flag, c->stage_f, c->stage_rho, c->stage_u, c->mm_acc, c->probe, c->tcount};
     for (void *b : bufs)
         if (b) cudaFree(b);
     if (c->ev_main) cudaEventDestroy(c->ev_main);
@@ -1391,8 +1336,6 @@ static int ctx_build(lbm_ctx *c, const lbm_bc_desc *bc)
     CK(cudaMalloc(&c->err_flag, 4));
     CK(cudaMemsetAsync(c->done_counter, 0, 8, c->stream));
     CK(cudaMemsetAsync(c->err_flag, 0, 4, c->stream));
-    CK(cudaMalloc(&c->bar, 8));
-    CK(cudaMemsetAsync(c->bar, 0, 8, c->stream));
     CK(cudaMalloc(&c->mm_acc, 32));
     CK(cudaMalloc(&c->tcount, 24));
     CK(cudaMemsetAsync(c->tcount, 0, 24, c->stream));
@@ -1485,7 +1428,6 @@ extern "C" int lbm_create(int device, int nx, int ny, int ghost_x, int ghost_y, 
     if (const char *g = getenv("LBM_GENERIC_KERNEL")) c->force_generic = atoi(g) != 0;
     if (const char *g = getenv("LBM_NO_GRAPHS")) c->use_graphs = atoi(g) == 0;
     if (const char *g = getenv("LBM_NO_FUSED")) c->use_fused = atoi(g) == 0;
-    if (const char *g = getenv("LBM_NO_PERSISTENT")) c->use_persistent = atoi(g) == 0;
     if (const char *g = getenv("LBM_FUSED_SEG")) c->fused_seg = atoi(g) >= 2 ? atoi(g) : 0;
     if (const char *t = getenv("LBM_HALO_TIMEOUT_S")) c->timeout_cycles = (long long)(atof(t) * 2e9);
     if (int rc = ctx_build(c, bc)) {
@@ -1513,8 +1455,6 @@ extern "C" int lbm_set_option(lbm_ctx *c, const char *name, int value)
         c->use_fused = value != 0;
     else if (n == "graphs")
         c->use_graphs = value != 0;
-    else if (n == "persistent")
-        c->use_persistent = value != 0;
     else if (n == "generic_kernel")
         c->force_generic = value != 0;
     else if (n == "fused_exact")
@@ -1526,7 +1466,7 @@ extern "C" int lbm_set_option(lbm_ctx *c, const char *name, int value)
         if (value < 2 && value != 0) return fail(LBM_ERR_ARG, "lbm_set_option: fused_seg must be >= 2, or 0 for the default");
         c->fused_seg = value;
     } else
-        return fail(LBM_ERR_ARG, "lbm_set_option: unknown option '%s' (fused, graphs, persistent, generic_kernel, fused_exact, fused_seg, l2_prefetch)", name);
+        return fail(LBM_ERR_ARG, "lbm_set_option: unknown option '%s' (fused, graphs, generic_kernel, fused_exact, fused_seg, l2_prefetch)", name);
     return LBM_OK;
 }
 
@@ -1922,67 +1862,12 @@ extern "C" int lbm_init_equilibrium(lbm_ctx *c, const double *rho_x, const doubl
     return end_load(c, omega);
 }
 
-// ---- many steps per cooperative launch on launch-bound lattices ------------------------------------------------
-template <bool MASK, bool HALO>
-static int multi_launch(lbm_ctx *c, MultiParams &M, int threads, int *cache)
-{
-    if (*cache == 0) {
-        int coop = 0, per_sm = 0, sms = 0;
-        CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device));
-        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_multi<MASK, HALO>, 256, 0));
-        *cache = coop && per_sm > 0 ? per_sm * sms : -1;
-    }
-    if (*cache < 0) return LBM_ERR_STATE;   // caller falls back to graphs / single launches
-    const int blocks = std::min(M.n_rows, *cache);
-    void *args[] = {&M};
-    cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_multi<MASK, HALO>, dim3(blocks), dim3(threads), args, 0, c->stream);
-    if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "cooperative multi-step launch failed: %s", cudaGetErrorString(e));
-    c->launches++;
-    return LBM_OK;
-}
-
-static bool multi_ok(const lbm_ctx *c)
-{
-    return c->use_persistent && !c->any_remote && (long long)c->NX * c->NY < kEdgeThreshold && (!c->has_bc || use_mask(c)) &&
-           (!(c->gx || c->gy) || c->halo_ready);
-}
-
-// n steps from S[cur] in one launch. Returns LBM_ERR_STATE (without an error message) when cooperative launches are
-// not available on this device.
-static int multi_steps(lbm_ctx *c, double omega, int n)
-{
-    MultiParams M;
-    memset(&M, 0, sizeof M);
-    const bool mask = use_mask(c), halo = c->halo_ready;
-    for (int k = 0; k < 2; k++) {
-        const int src = c->cur ^ k, dst = src ^ 1;
-        StepParams &P = M.P[k];
-        fill_common(c, P, src, dst, omega);
-        fill_halo(c, P, dst, false);
-        set_probe(c, P, src, dst);
-        P.row0a = c->gx;
-        P.y0 = c->gy;
-        P.y1 = c->NY - c->gy;
-    }
-    M.n_steps = n;
-    M.n_rows = c->NX - 2 * c->gx;
-    M.bar_count = c->bar;
-    M.bar_gen = c->bar + 1;
-    M.gen0 = c->bar_gen;
-    const int threads = block_size(c->NY - 2 * c->gy);
-    int rc;
-    if (mask)
-        rc = halo ? multi_launch<true, true>(c, M, threads, &c->coop_blocks[3]) : multi_launch<true, false>(c, M, threads, &c->coop_blocks[2]);
-    else
-        rc = halo ? multi_launch<false, true>(c, M, threads, &c->coop_blocks[1]) : multi_launch<false, false>(c, M, threads, &c->coop_blocks[0]);
-    if (rc == LBM_OK) c->bar_gen += (unsigned)(n - 1);
-    return rc;
-}
-
 // ---- CUDA graphs for launch-bound lattices ----------------------------------------------------------------
 // Configs 1-4 of BASELINE.json are <= 77 k cells: a step is 2-5 us of GPU work behind ~2 us of launch gap. A graph of
 // kGraphSteps captured steps is replayed instead; kGraphSteps is even, so the A/B parity is the same before and after.
+// (Tried and dropped: all steps in ONE cooperative launch with a grid barrier — atomic counter + generation word —
+//  after every step. Bit-exact, but the barrier costs more than a kernel boundary inside a graph: +1.1 us per step on
+//  every lattice from 100x50 to 1000x1000, profiles/r01e_persistent_vs_graph.txt.)
 static const int kGraphSteps = 32;
 
 static void drop_graphs(lbm_ctx *c)
@@ -2038,18 +1923,6 @@ extern "C" int lbm_step(lbm_ctx *c, double omega, int n_steps)
         c->omega = omega;
     }
     int left = n_steps;
-    if (multi_ok(c) && left >= 4) {
-        while (left > 0) {
-            const int n = std::min(left, 1 << 14);
-            const int rc = multi_steps(c, omega, n);
-            if (rc == LBM_ERR_STATE) break;   // no cooperative launch here: graphs / single launches below
-            if (rc) return rc;
-            c->cur ^= n & 1;
-            c->t += n;
-            left -= n;
-            c->prev_is_tm1 = true;
-        }
-    }
     if (c->use_graphs && !c->any_remote && (long long)c->NX * c->NY < kEdgeThreshold && left >= 2 * kGraphSteps) {
         lbm_ctx::GraphEntry *g = nullptr;
         if (int rc = graph_for(c, omega, &g)) return rc;
@@ -2094,8 +1967,6 @@ extern "C" int lbm_sync(lbm_ctx *c)
         cudaMemcpy(fl, c->flags_in, sizeof fl, cudaMemcpyDeviceToHost);
         cudaMemsetAsync(c->err_flag, 0, 4, c->stream);
         cudaStreamSynchronize(c->stream);
-        if ((err & 0xC0000000u) == 0xC0000000u)
-            return fail(LBM_ERR_TIMEOUT, "the grid barrier of the multi-step kernel timed out (blocks of a cooperative launch not co-resident?): results are invalid, load the state again");
         return fail(LBM_ERR_TIMEOUT,
                     "halo flag wait timed out: a neighbouring rank did not take the same step (waited for step %u of "
                     "neighbour slot %u; flags now %u %u %u %u . %u %u %u %u; my step count %u)",

@@ -628,59 +628,6 @@ def test_boundary_rows_everywhere_stay_on_one_step_per_pass(P, oracle):
     lat.close()
 
 
-@pytest.mark.parametrize('scenario', ['periodic', 'periodic_odd', 'couette', 'poiseuille', 'karman_ghost'])
-def test_many_steps_per_cooperative_launch(P, oracle, scenario):
-    """Launch-bound lattices take n steps in ONE cooperative launch (k_multi: resident blocks, a grid barrier per
-    step). Must equal single-step launches and the C oracle bit for bit — fields, ghost ring, probe ring."""
-    from lattice_boltzmann_parallel_solver_b200.engine import Lattice
-    BU = P.boundary_utils
-    omega, ghost, km = 1.1, (0, 0), None
-    if scenario == 'periodic':
-        shape, sc = (100, 50), oracle.c.periodic()
-    elif scenario == 'periodic_odd':
-        shape, sc = (37, 301), oracle.c.periodic()
-    elif scenario == 'couette':
-        shape, sc = (100, 100), oracle.c.couette(0.05, 1.0)
-        km = BU.couette_flow_boundary_conditions(*shape, 0.05, 1.0).kind_map(shape)
-    elif scenario == 'poiseuille':
-        shape, sc = (100, 50), oracle.c.poiseuille(0.3338, 0.3328)
-        km = BU.poiseuille_flow_boundary_conditions(*shape, 0.3338, 0.3328).kind_map(shape)
-    else:
-        shape, ghost, omega = (422, 182), (1, 1), 1.6
-        sc = oracle.c.karman(420, 180, 1.0, 0.1, 40, ghost=1)
-        km = BU.parallel_von_karman_boundary_conditions([0, 0], 420, 180, 420, 180, 1, 1, 1.0, 0.1, 40).kind_map(shape)
-    f, rho, u = random_state(oracle, shape, 8)
-    px, py = shape[0] - 2, 1
-    lats = []
-    for persistent in (1, 0):
-        lat = Lattice(*shape, km, ghost=ghost)
-        if ghost[0]:
-            lat.connect_self_periodic()
-        lat.set_option('persistent', persistent)
-        lat.probe(px, py, capacity=128)
-        lat.load(f, rho, u, omega)
-        l0 = lat.launches
-        for n in (37, 4, 3, 70):
-            lat.run(n)
-        lats.append((lat, lat.launches - l0))
-    (multi, lm), (single, ls) = lats
-    assert lm == 1 + 1 + 3 + 1, f'{lm} launches: the multi-step kernel was not used'
-    assert ls >= 114
-    got = multi.fields()
-    for a, b, nm in zip(got, single.fields(), 'f rho u'.split()):
-        assert_parity(a, b, f'{scenario} {nm}')
-    assert_parity(multi.probe_read(1, 114), single.probe_read(1, 114), 'probe ring')
-    ref = oracle.c.run(f, rho, u, omega, sc, 114)
-    for a, b, nm in zip(got, ref, 'f rho u'.split()):
-        assert_parity(a, b, f'{scenario} vs oracle {nm}')
-    multi.run(1, 0.9)                                       # omega change after a multi-step launch: redo from S_{t-1}
-    single.run(1, 0.9)
-    for a, b, nm in zip(multi.fields(), single.fields(), 'f rho u'.split()):
-        assert_parity(a, b, f'{scenario} omega change {nm}')
-    multi.close()
-    single.close()
-
-
 def test_options_and_state_errors(P, oracle):
     from lattice_boltzmann_parallel_solver_b200 import _native as N
     from lattice_boltzmann_parallel_solver_b200.engine import Lattice
