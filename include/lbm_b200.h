@@ -126,6 +126,8 @@ int lbm_set_bc_mode(lbm_ctx *ctx, int mode);
  *                    the other rows two one-step mask launches through a strip window (needs ghost_x = ghost_y = 0,
  *                    no pressure-periodic rows, and boundary cells on at most half of the rows)
  *   "graphs"         CUDA-graph replay of 32 captured steps on launch-bound lattices
+ *   "pdl"            programmatic dependent launch between the step kernels of launch-bound lattices: the next step's
+ *                    blocks are launched and read their parameters / kind bytes while the current step still runs
  *   "generic_kernel" force the one-cell-per-thread step kernel
  *   "fused_exact"    (default 0) an even lbm_step(n) is exactly n/2 two-step passes without the one-step tail that
  *                    normally ends every call; results cannot be materialised until one more single step is taken

@@ -402,12 +402,17 @@ __device__ __forceinline__ void rule_cell(const StepParams &P, int x, int y, uns
     finish_cell<HALO, FINAL>(P, x, y, f, k.flags, k.skip_store);
 }
 
-// One cell of one step (or of a materialisation): kind byte -> rule path or plain pulls -> finish_cell
-template <bool MASK, bool HALO, bool FINAL>
-__device__ __forceinline__ void step_cell(const StepParams &P, int x, int y)
+// Programmatic dependent launch (launch-bound lattices, where a step is ~1 us of work behind ~1 us of launch
+// latency): a step kernel releases its dependents at once, so the next step's blocks are launched, read their
+// parameters and their kind byte while this step still runs, and then wait here for this grid to complete and
+// flush before they touch S. Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// One cell of one step (or of a materialisation): rule path or plain pulls -> finish_cell
+template <bool HALO, bool FINAL>
+__device__ __forceinline__ void step_cell(const StepParams &P, int x, int y, unsigned kind)
 {
-    unsigned kind = 0;
-    if (MASK) kind = P.kind_map[(long long)x * P.pitch + y];
     if (kind != 0) {
         rule_cell<HALO, FINAL>(P, x, y, kind);
     } else {
@@ -431,7 +436,7 @@ __device__ __forceinline__ void step_cell(const StepParams &P, int x, int y)
 template <bool MASK, bool HALO, bool FINAL, bool LIST>
 __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepParams P)
 {
-    if (HALO && !FINAL) halo_wait(P);
+    pdl_release();
     int x, y;
     bool active = true;
     if (LIST) {
@@ -446,7 +451,11 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepParams
         y = P.y0 + cb * blockDim.x + threadIdx.x;
         active = y < P.y1;
     }
-    if (active) step_cell<MASK || LIST, HALO, FINAL>(P, x, y);
+    unsigned kind = 0;   // the kind map is written once, at lbm_create: safe to read before the previous step is complete
+    if ((MASK || LIST) && active) kind = P.kind_map[(long long)x * P.pitch + y];
+    pdl_wait();
+    if (HALO && !FINAL) halo_wait(P);
+    if (active) step_cell<HALO, FINAL>(P, x, y, kind);
     if (HALO && !FINAL) halo_signal(P);
 }
 
@@ -471,6 +480,8 @@ __device__ __forceinline__ void st2(double *p, double a, double b)
 
 __global__ void __launch_bounds__(256) k_step_pair(const __grid_constant__ StepParams P)
 {
+    pdl_release();
+    pdl_wait();
     const int x = P.row0a + blockIdx.y;
     const int y = 2 * (blockIdx.x * blockDim.x + threadIdx.x);   // cells y, y+1; NY is even
     if (y >= P.NY) return;
@@ -1018,6 +1029,7 @@ struct lbm_ctx {
     };
     std::vector<GraphEntry> graphs;
     bool use_graphs = true;
+    bool pdl = true;              // programmatic dependent launch between the step kernels of launch-bound lattices (option "pdl")
     bool use_fused = true;        // LBM_NO_FUSED=1: one step per pass only (A/B measurements)
     int l2_prefetch = 2;          // rows ahead whose source segments k_step2x prefetches into L2 (option "l2_prefetch")
     int fused_seg = 0;            // output rows per block of the two-step kernel; 0 = pick_seg (LBM_FUSED_SEG / option "fused_seg")
@@ -1455,6 +1467,10 @@ extern "C" int lbm_set_option(lbm_ctx *c, const char *name, int value)
         c->use_fused = value != 0;
     else if (n == "graphs")
         c->use_graphs = value != 0;
+    else if (n == "pdl") {
+        c->pdl = value != 0;
+        drop_graphs(c);
+    }
     else if (n == "generic_kernel")
         c->force_generic = value != 0;
     else if (n == "fused_exact")
@@ -1466,7 +1482,7 @@ extern "C" int lbm_set_option(lbm_ctx *c, const char *name, int value)
         if (value < 2 && value != 0) return fail(LBM_ERR_ARG, "lbm_set_option: fused_seg must be >= 2, or 0 for the default");
         c->fused_seg = value;
     } else
-        return fail(LBM_ERR_ARG, "lbm_set_option: unknown option '%s' (fused, graphs, generic_kernel, fused_exact, fused_seg, l2_prefetch)", name);
+        return fail(LBM_ERR_ARG, "lbm_set_option: unknown option '%s' (fused, graphs, pdl, generic_kernel, fused_exact, fused_seg, l2_prefetch)", name);
     return LBM_OK;
 }
 
@@ -1562,12 +1578,35 @@ static void fill_halo(const lbm_ctx *c, StepParams &P, int dst_buf, bool flags)
 
 static int block_size(int w) { return w >= 256 ? 256 : std::max(32, (w + 31) & ~31); }
 
-template <bool MASK, bool HALO, bool FINAL, bool LIST>
-static cudaError_t launch(const StepParams &P, int blocks, int threads, cudaStream_t st)
+// pdl: launch with programmatic stream serialization (see pdl_release / pdl_wait); captured into a graph this becomes a
+// programmatic dependency edge
+template <class... Args>
+static cudaError_t launch_kernel(void (*kernel)(Args...), dim3 grid, dim3 block, cudaStream_t st, bool pdl, const StepParams &P)
 {
-    k_step<MASK, HALO, FINAL, LIST><<<blocks, threads, 0, st>>>(P);
-    return cudaGetLastError();
+    if (!pdl) {
+        kernel<<<grid, block, 0, st>>>(P);
+        return cudaGetLastError();
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, P);
 }
+
+template <bool MASK, bool HALO, bool FINAL, bool LIST>
+static cudaError_t launch(const StepParams &P, int blocks, int threads, cudaStream_t st, bool pdl = false)
+{
+    return launch_kernel(k_step<MASK, HALO, FINAL, LIST>, dim3(blocks), dim3(threads), st, pdl, P);
+}
+
+// launch-bound lattices without remote neighbours chain their step kernels with programmatic dependent launches
+static bool use_pdl(const lbm_ctx *c) { return c->pdl && !c->any_remote && (long long)c->NX * c->NY < kEdgeThreshold; }
 
 static int rows_launch(lbm_ctx *c, StepParams P, int row0a, int na, int row0b, int nb, bool mask, bool halo, cudaStream_t st)
 {
@@ -1586,12 +1625,13 @@ static int rows_launch(lbm_ctx *c, StepParams P, int row0a, int na, int row0b, i
         // bandwidth kernel: two cells per thread, 2-D grid
         const int pairs = c->NY / 2, pbs = pairs >= 128 ? 128 : std::max(32, (pairs + 31) & ~31);
         dim3 grid((pairs + pbs - 1) / pbs, na);
-        k_step_pair<<<grid, pbs, 0, st>>>(P);
-        e = cudaGetLastError();
+        // (the pair kernel has no prologue to overlap: early-launched blocks only take slots away below ~2^17 cells,
+        //  profiles/r01e_small_lattices_pdl.txt)
+        e = launch_kernel(k_step_pair, grid, dim3(pbs), st, use_pdl(c) && (long long)c->NX * c->NY >= (1 << 17), P);
     } else if (mask)
-        e = halo ? launch<true, true, false, false>(P, blocks, bs, st) : launch<true, false, false, false>(P, blocks, bs, st);
+        e = halo ? launch<true, true, false, false>(P, blocks, bs, st, use_pdl(c)) : launch<true, false, false, false>(P, blocks, bs, st, use_pdl(c));
     else
-        e = halo ? launch<false, true, false, false>(P, blocks, bs, st) : launch<false, false, false, false>(P, blocks, bs, st);
+        e = halo ? launch<false, true, false, false>(P, blocks, bs, st, use_pdl(c)) : launch<false, false, false, false>(P, blocks, bs, st, use_pdl(c));
     if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "step kernel launch failed: %s", cudaGetErrorString(e));
     c->launches++;
     return LBM_OK;
@@ -1646,7 +1686,7 @@ static int one_step(lbm_ctx *c, int src, double omega, long long t_new)
         L.signal_value = remote ? E + 1 : 0;
         const int blocks = (c->n_cells + 127) / 128;
         L.n_blocks = blocks;
-        cudaError_t e = halo ? launch<true, true, false, true>(L, blocks, 128, c->stream) : launch<true, false, false, true>(L, blocks, 128, c->stream);
+        cudaError_t e = halo ? launch<true, true, false, true>(L, blocks, 128, c->stream, use_pdl(c)) : launch<true, false, false, true>(L, blocks, 128, c->stream, use_pdl(c));
         if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "edge kernel launch failed: %s", cudaGetErrorString(e));
         c->launches++;
     }
