@@ -394,9 +394,8 @@ __device__ __forceinline__ void finish_cell(const StepParams &P, int x, int y, c
 // out-of-line rule interpreter through an array reference, which put f[9] of EVERY cell in local memory and
 // doubled the DRAM writes of the mask kernel (profiles/r01_summary.md).
 template <bool HALO, bool FINAL>
-__device__ __forceinline__ void rule_cell(const StepParams &P, int x, int y, unsigned kind)
+__device__ __forceinline__ void rule_cell(const StepParams &P, int x, int y, const lbm_kind &k)
 {
-    const lbm_kind k = P.kinds[kind];
     double f[9];
     pull_rules(P, k, x, y, f);
     finish_cell<HALO, FINAL>(P, x, y, f, k.flags, k.skip_store);
@@ -411,10 +410,10 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 
 // One cell of one step (or of a materialisation): rule path or plain pulls -> finish_cell
 template <bool HALO, bool FINAL>
-__device__ __forceinline__ void step_cell(const StepParams &P, int x, int y, unsigned kind)
+__device__ __forceinline__ void step_cell(const StepParams &P, int x, int y, unsigned kind, const lbm_kind &k)
 {
     if (kind != 0) {
-        rule_cell<HALO, FINAL>(P, x, y, kind);
+        rule_cell<HALO, FINAL>(P, x, y, k);
     } else {
         double f[9];
         if (FINAL && P.use_snap) {
@@ -451,11 +450,16 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepParams
         y = P.y0 + cb * blockDim.x + threadIdx.x;
         active = y < P.y1;
     }
-    unsigned kind = 0;   // the kind map is written once, at lbm_create: safe to read before the previous step is complete
-    if ((MASK || LIST) && active) kind = P.kind_map[(long long)x * P.pitch + y];
+    // the kind map and the kind table are written once, at lbm_create: safe to read before the previous step is complete
+    unsigned kind = 0;
+    lbm_kind k = {};
+    if ((MASK || LIST) && active) {
+        kind = P.kind_map[(long long)x * P.pitch + y];
+        if (kind) k = P.kinds[kind];
+    }
     pdl_wait();
     if (HALO && !FINAL) halo_wait(P);
-    if (active) step_cell<HALO, FINAL>(P, x, y, kind);
+    if (active) step_cell<HALO, FINAL>(P, x, y, kind, k);
     if (HALO && !FINAL) halo_signal(P);
 }
 
