@@ -93,6 +93,13 @@ typedef struct {
  * (src/lattice_boltzmann_method.py:122-133) and of the norm in equilibrium_distr_func (:185). */
 int lbm_selftest_arith(int device, int64_t n, uint64_t seed, uint64_t out[5]);
 
+/* Test hook, host only (no CUDA call): the row plan of the two-steps-per-pass schedule on a lattice with boundary
+ * cells. row_has_boundary[x] != 0 marks rows that hold a non-fluid cell. Out: strips[2i], strips[2i+1] = rows [a, b)
+ * (b may exceed nx: the strip wraps) advanced by two one-step mask launches through a window; clean[2i], clean[2i+1] =
+ * row ranges of the two-step kernel. n_strips = n_clean = -1: the lattice stays on one step per pass (boundary rows
+ * within two rows of more than half of all rows, more than 16 ranges, or nx < 16). Arrays need room for 16 ranges. */
+int lbm_plan_two_step(int nx, const uint8_t *row_has_boundary, int *n_strips, int *strips, int *n_clean, int *clean);
+
 /* Applies the closures' effect to host arrays (used when a boundary closure is CALLED directly, as the
  * reference's tests/test_boundary_conditions.py does). f_post is updated in place; f_prev may be NULL when no
  * OUTLET rule is present. PBC source flags are ignored here — use lbm_pbc_apply. */

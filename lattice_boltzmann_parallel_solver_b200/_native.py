@@ -67,6 +67,8 @@ SIGNATURES = {
     'lbm_velocity': (C.c_int, [C.c_int, C.c_int64, _DP, _DP, _DP]),
     'lbm_streaming': (C.c_int, [C.c_int, C.c_int, C.c_int, _DP, _DP]),
     'lbm_selftest_arith': (C.c_int, [C.c_int, C.c_int64, C.c_uint64, C.POINTER(C.c_uint64)]),
+    'lbm_plan_two_step': (C.c_int, [C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                    C.POINTER(C.c_int)]),
     'lbm_bc_apply': (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(BcDesc), _DP, _DP, _DP]),
     'lbm_pbc_apply': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _DP, _DP, _DP]),
     'lbm_create': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(BcDesc), C.POINTER(_CTX)]),

@@ -1267,26 +1267,26 @@ extern "C" int lbm_destroy(lbm_ctx *c)
 // pulls, which is all k_step2x knows. Maximal runs of the other rows are STRIPS; a strip [a, b) is advanced by the
 // one-step mask kernel twice, S_t rows [a-2, b+2) -> window rows [a-1, b+1) of S_{t+1} -> S_{t+2} rows [a, b).
 // For the von Karman rule set (inlet row, plate rows, outlet rows) 13 of the NX rows are strip rows.
-static int plan_strips(lbm_ctx *c, const std::vector<int2> &cells)
+// (pure host logic; lbm_plan_two_step exposes it to the CPU tests)
+static bool plan_rows(int NX, const std::vector<char> &dirty, std::vector<std::pair<int, int>> &strips,
+                      std::vector<std::pair<int, int>> &clean)
 {
-    const int NX = c->NX;
-    if (NX < 16) return LBM_OK;
-    std::vector<char> dirty(NX, 0), strip_row(NX, 0);
-    for (const int2 &xy : cells) dirty[xy.x] = 1;
+    strips.clear();
+    clean.clear();
+    if (NX < 16) return false;
+    std::vector<char> strip_row(NX, 0);
     int n_strip_rows = 0;
     for (int x = 0; x < NX; x++) {
         for (int d = -2; d <= 2; d++) strip_row[x] |= dirty[((x + d) % NX + NX) % NX];
         n_strip_rows += strip_row[x];
     }
-    if (2 * n_strip_rows > NX) return LBM_OK;   // mostly boundary rows (walls along x, ...): one step per pass
-    std::vector<lbm_ctx::Strip> strips;
+    if (2 * n_strip_rows > NX) return false;   // mostly boundary rows (walls along x, ...): one step per pass
     for (int a = 0; a < NX; a++) {
         if (!strip_row[a] || strip_row[(a + NX - 1) % NX]) continue;   // a strip begins after a clean row
         int b = a;
         while (strip_row[b % NX]) b++;
-        strips.push_back({a, b, nullptr});
+        strips.push_back({a, b});   // b may exceed NX: the strip wraps
     }
-    std::vector<std::pair<int, int>> clean;
     for (int x = 0; x < NX;) {
         if (strip_row[x]) {
             x++;
@@ -1297,18 +1297,47 @@ static int plan_strips(lbm_ctx *c, const std::vector<int2> &cells)
         clean.push_back({x, e});
         x = e;
     }
-    if (strips.size() > 16 || clean.size() > 16) return LBM_OK;
-    for (auto &s : strips) {
+    return strips.size() <= 16 && clean.size() <= 16;
+}
+
+extern "C" int lbm_plan_two_step(int nx, const uint8_t *row_has_boundary, int *n_strips, int *strips, int *n_clean, int *clean)
+{
+    if (nx < 1 || !row_has_boundary || !n_strips || !strips || !n_clean || !clean) return fail(LBM_ERR_ARG, "lbm_plan_two_step: bad argument");
+    std::vector<char> dirty(row_has_boundary, row_has_boundary + nx);
+    std::vector<std::pair<int, int>> st, cl;
+    if (!plan_rows(nx, dirty, st, cl)) {
+        *n_strips = *n_clean = -1;
+        return LBM_OK;
+    }
+    *n_strips = (int)st.size();
+    *n_clean = (int)cl.size();
+    for (size_t i = 0; i < st.size(); i++) {
+        strips[2 * i] = st[i].first;
+        strips[2 * i + 1] = st[i].second;
+    }
+    for (size_t i = 0; i < cl.size(); i++) {
+        clean[2 * i] = cl[i].first;
+        clean[2 * i + 1] = cl[i].second;
+    }
+    return LBM_OK;
+}
+
+static int plan_strips(lbm_ctx *c, const std::vector<int2> &cells)
+{
+    std::vector<char> dirty(c->NX, 0);
+    for (const int2 &xy : cells) dirty[xy.x] = 1;
+    std::vector<std::pair<int, int>> rows, clean;
+    if (!plan_rows(c->NX, dirty, rows, clean)) return LBM_OK;
+    for (const auto &r : rows) {
+        lbm_ctx::Strip s = {r.first, r.second, nullptr};
         const size_t bytes = (size_t)9 * (s.b - s.a + 2) * c->pitch * 8;
         if (cudaMalloc(&s.buf, bytes) != cudaSuccess) {
             cudaGetLastError();
-            for (auto &q : strips)
-                if (q.buf) cudaFree(q.buf);
             return fail(LBM_ERR_NOMEM, "cannot allocate %.1f MB for a boundary strip window", bytes / 1e6);
         }
+        c->strips.push_back(s);   // owned by the context from here on (lbm_destroy frees it)
         CK(cudaMemsetAsync(s.buf, 0, bytes, c->stream));
     }
-    c->strips = strips;
     c->clean = clean;
     c->fused_bc = true;
     return LBM_OK;

@@ -282,3 +282,67 @@ def test_cpu_baseline_processes_equal_one_process():
     assert line.returncode == 0, line.stderr[-2000:]
     d = json.loads(line.stdout.strip().splitlines()[-1])
     assert d['impl'] == 'reference' and d['value'] > 0 and d['cpu_baseline']['kind'] == 'port' and d['e2e']['value'] == d['value']
+
+
+# ---------------------------------------------------------------------------------------------------------
+# row plan of the two-steps-per-pass schedule on lattices with boundary cells (host logic of the C library)
+# ---------------------------------------------------------------------------------------------------------
+def _plan(nx, dirty_rows):
+    from lattice_boltzmann_parallel_solver_b200 import _native as N
+    lib = N.load()
+    flags = (ctypes.c_uint8 * nx)()
+    for r in dirty_rows:
+        flags[r] = 1
+    ns, nc = ctypes.c_int(), ctypes.c_int()
+    strips, clean = (ctypes.c_int * 32)(), (ctypes.c_int * 32)()
+    N.check(lib.lbm_plan_two_step(nx, flags, ctypes.byref(ns), strips, ctypes.byref(nc), clean))
+    if ns.value < 0:
+        return None
+    return ([(strips[2 * i], strips[2 * i + 1]) for i in range(ns.value)],
+            [(clean[2 * i], clean[2 * i + 1]) for i in range(nc.value)])
+
+
+def test_two_step_row_plan_known_cases():
+    nx = 16384
+    # von Karman rule set: inlet row 0, plate rows nx/4 and nx/4+1, outlet rows nx-2, nx-1 (bench.py karman_lattice)
+    strips, clean = _plan(nx, [0, 4096, 4097, nx - 2, nx - 1])
+    assert strips == [(4094, 4100), (nx - 4, nx + 3)]          # the outlet / inlet rows wrap into ONE strip
+    assert clean == [(3, 4094), (4100, nx - 4)]
+    assert _plan(nx, []) == ([], [(0, nx)])
+    assert _plan(nx, [8000]) == ([(7998, 8003)], [(0, 7998), (8003, nx)])
+    assert _plan(nx, [1]) == ([(nx - 1, nx + 4)], [(4, nx - 1)])
+    assert _plan(64, range(64)) is None                          # walls along x: every row is a boundary row
+    assert _plan(64, range(0, 64, 5)) is None                    # a boundary row within two rows of every row
+    assert _plan(8, [3]) is None                                 # too few rows
+    assert _plan(4096, range(0, 4096, 128)) is None              # 32 strips: more ranges than the schedule keeps
+
+
+def test_two_step_row_plan_properties():
+    """Every row is in exactly one strip or clean range; a clean row has no boundary row within two rows (periodic);
+    strips are maximal runs; ranges are sorted."""
+    rng = np.random.default_rng(4)
+    for trial in range(200):
+        nx = int(rng.integers(16, 400))
+        dirty = sorted(set(int(v) for v in rng.integers(0, nx, int(rng.integers(0, 6)))))
+        plan = _plan(nx, dirty)
+        near = np.zeros(nx, dtype=bool)
+        for r in dirty:
+            for d in range(-2, 3):
+                near[(r + d) % nx] = True
+        if plan is None:
+            assert 2 * near.sum() > nx, (nx, dirty)
+            continue
+        strips, clean = plan
+        owner = np.zeros(nx, dtype=int)
+        for a, b in strips:
+            assert 0 <= a < nx and a < b
+            for r in range(a, b):
+                owner[r % nx] += 1
+                assert near[r % nx]
+            assert not near[(a - 1) % nx] and not near[b % nx]   # maximal
+        for a, b in clean:
+            assert 0 <= a < b <= nx
+            owner[a:b] += 1
+            assert not near[a:b].any()
+        assert (owner == 1).all(), (nx, dirty, plan)
+        assert clean == sorted(clean) and strips == sorted(strips)
