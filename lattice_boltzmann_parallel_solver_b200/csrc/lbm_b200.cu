@@ -538,8 +538,9 @@ __global__ void __launch_bounds__(256) k_step_pair(const __grid_constant__ StepP
 // TWO time steps per pass (temporal blocking) on fluid rows: S_t -> S_{t+2} with ~73 B of DRAM traffic per cell
 // update instead of 144 B. A block of T threads owns output rows [x0, x1) x columns [y0, y0 + 2T-4) and marches
 // along x; every thread owns an aligned PAIR of columns of the intermediate state S_{t+1}:
-//   iteration j: pull row j of S_t from global (exactly the loads of k_step_pair, prefetched one row ahead),
-//                collide -> row j of S_{t+1}. The six populations that move along y go into a 4-slot shared-memory
+//   iteration j: pull row j of S_t from global (exactly the loads of k_step_pair; issued half an iteration ahead
+//                into the registers row j-1 has just freed, after one thread per block has bulk-prefetched the
+//                source segments of row j+2 into L2), collide -> row j of S_{t+1}. The six populations that move along y go into a 4-slot shared-memory
 //                ring as 128-bit stores; the three that do not (0, 1, 3) never leave the thread's registers.
 //                One __syncthreads; then row j-1 of S_{t+2} is pulled from ring rows j-2, j-1, j (the +-1 column
 //                shifts are shared-memory offsets), collided and written with 128-bit stores.
