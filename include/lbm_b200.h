@@ -174,8 +174,11 @@ int lbm_materialize(lbm_ctx *ctx, double *f, double *rho, double *u);
 /* Same for the sub-rectangle [x0,x1) x [y0,y1) (row-major, packed). */
 int lbm_materialize_region(lbm_ctx *ctx, int x0, int x1, int y0, int y1, double *f, double *rho, double *u);
 
-/* Probe: records (u_x, u_y) at one cell after every step into a device ring (experiments.py:703-704).
- * lbm_probe_read copies the samples of steps [t0, t0+n) — at most `capacity` behind lbm_time(). Synchronous. */
+/* Probe: records (u_x, u_y) at one cell after every step (experiments.py:703-704) into a ring in host-mapped
+ * memory — the cell's thread stores the sample, a system-scope fence and the step number straight to the host as
+ * the step completes. lbm_probe_read copies the samples of steps [t0, t0+n) — at most `capacity` behind
+ * lbm_time() — and waits only until step t0+n-1 has reported: steps queued behind it keep running (choose
+ * capacity >= the number of steps queued ahead of the reader). */
 int lbm_probe_config(lbm_ctx *ctx, int x, int y, int capacity);
 int lbm_probe_read(lbm_ctx *ctx, int64_t t0, int n, double *uxuy);
 /* Whole-field extrema of the current state (experiments.py:181-193): out = {min rho, max rho, min u, max u}

@@ -88,7 +88,8 @@ struct StepParams {
     double *out_next;          // written by OUTLET_SRC cells
     double rho_in, rho_out;
     int px, py;
-    double *probe;             // ring of (ux, uy), probe_cap entries, or null
+    double *probe;             // ring of (ux, uy), probe_cap entries, in host-mapped memory, or null
+    long long *progress;       // host-mapped: time of the newest sample in the ring (lbm_probe_read polls it)
     const long long *tc_in;    // device-resident time of the state read (captured graphs need no new params) ...
     long long *tc_out;         // ... and of the state written; both point into lbm_ctx::tcount
     int probe_cap;
@@ -342,6 +343,15 @@ __device__ __forceinline__ void halo_signal(const StepParams &P)
 // -------------------------------------------------------------------------------------------------------
 // Probe (experiments.py:703-704): the one thread that owns the probe cell appends (ux, uy) of the new time to the
 // ring and advances the device-side time counter of the destination buffer.
+// The ring lives in host-mapped memory: the sample travels to the host as the step that produced it completes, and
+// the host reads it without a CUDA call while the device runs on (lbm_probe_read). The sample(s) first, then a
+// system-scope fence, then the time word the host polls.
+__device__ __forceinline__ void publish_progress(const StepParams &P, long long t_new)
+{
+    __threadfence_system();
+    *(volatile long long *)P.progress = t_new;
+}
+
 __device__ __forceinline__ void record_probe(const StepParams &P, double ux, double uy)
 {
     const long long t_new = __ldcg(P.tc_in) + 1;
@@ -349,6 +359,7 @@ __device__ __forceinline__ void record_probe(const StepParams &P, double ux, dou
     slot[0] = ux;
     slot[1] = uy;
     *P.tc_out = t_new;
+    publish_progress(P, t_new);
 }
 
 // Everything one cell does after its nine f_post values are known (shared by the register-resident fluid path
@@ -666,6 +677,7 @@ __global__ void __launch_bounds__(T, 4) k_step2x(const __grid_constant__ StepPar
                 slot[0] = ux;
                 slot[1] = uy;
                 *P.tc_out = tc + 2;
+                publish_progress(P, tc + 2);   // (this thread also wrote the sample of t+1, in first_step)
             }
             eq_poly(ux, uy, p);
             eq_from_poly(rho, p, e);
@@ -676,6 +688,7 @@ __global__ void __launch_bounds__(T, 4) k_step2x(const __grid_constant__ StepPar
                 slot[0] = ux;
                 slot[1] = uy;
                 *P.tc_out = tc + 2;
+                publish_progress(P, tc + 2);   // (this thread also wrote the sample of t+1, in first_step)
             }
             eq_poly(ux, uy, p);
             eq_from_poly(rho, p, e);
@@ -1022,7 +1035,8 @@ struct lbm_ctx {
     long long *mm_acc = nullptr;
     // probe ring
     int px = -1, py = -1, probe_cap = 0;
-    double *probe = nullptr;
+    double *probe = nullptr;         // cudaHostAlloc (mapped): written by the probe cell's thread, read by the host
+    long long *progress = nullptr;   // cudaHostAlloc (mapped)
     long long *tcount = nullptr;   // device [3]: time of the state in S[0], S[1], and in the strip windows
     // CUDA graphs of kGraphSteps steps for launch-bound lattices, keyed by (omega, parity, probe, bc mode)
     struct GraphEntry {
@@ -1252,9 +1266,11 @@ extern "C" int lbm_destroy(lbm_ctx *c)
     for (auto &s : c->strips)
         if (s.buf) cudaFree(s.buf);
     void *bufs[] = {c->arena,  c->kind_map, c->kinds,    c->ktab,   c->ctab,  c->outbuf[0],   c->outbuf[1], c->outbuf[2], c->cells, c->snap_row, c->snap_col,
-                    c->done_counter, c->err_flag, c->stage_f, c->stage_rho, c->stage_u, c->mm_acc, c->probe, c->tcount};
+                    c->done_counter, c->err_flag, c->stage_f, c->stage_rho, c->stage_u, c->mm_acc, c->tcount};
     for (void *b : bufs)
         if (b) cudaFree(b);
+    if (c->probe) cudaFreeHost(c->probe);
+    if (c->progress) cudaFreeHost(c->progress);
     if (c->ev_main) cudaEventDestroy(c->ev_main);
     if (c->ev_edge) cudaEventDestroy(c->ev_edge);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -1385,6 +1401,8 @@ static int ctx_build(lbm_ctx *c, const lbm_bc_desc *bc)
     CK(cudaMalloc(&c->mm_acc, 32));
     CK(cudaMalloc(&c->tcount, 24));
     CK(cudaMemsetAsync(c->tcount, 0, 24, c->stream));
+    CK(cudaHostAlloc((void **)&c->progress, 64, cudaHostAllocMapped));
+    *c->progress = 0;
     for (int b = 0; b < 3; b++) {
         CK(cudaMalloc(&c->outbuf[b], (size_t)3 * c->pitch * 8));
         CK(cudaMemsetAsync(c->outbuf[b], 0, (size_t)3 * c->pitch * 8, c->stream));
@@ -1574,6 +1592,7 @@ static void set_probe(const lbm_ctx *c, StepParams &P, int tc_in, int tc_out)
     P.px = c->px;
     P.py = c->py;
     P.probe = c->probe;
+    P.progress = c->progress;
     P.probe_cap = c->probe_cap;
     P.tc_in = c->tcount + tc_in;
     P.tc_out = c->tcount + tc_out;
@@ -1882,6 +1901,7 @@ static int end_load(lbm_ctx *c, double omega)
 {
     CK(cudaMemsetAsync(c->tcount, 0, 24, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    *c->progress = 0;
     c->loaded = true;
     c->t = 0;
     c->prev_is_tm1 = false;
@@ -2135,11 +2155,13 @@ extern "C" int lbm_probe_config(lbm_ctx *c, int x, int y, int capacity)
     if (!c) return fail(LBM_ERR_ARG, "lbm_probe_config: null context");
     if (x < 0 || y < 0 || x >= c->NX || y >= c->NY || capacity < 1) return fail(LBM_ERR_ARG, "lbm_probe_config: probe outside the lattice or capacity < 1");
     CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream_edge));
     CK(cudaStreamSynchronize(c->stream));
-    if (c->probe) CK(cudaFree(c->probe));
+    if (c->probe) CK(cudaFreeHost(c->probe));
     c->probe = nullptr;
-    CK(cudaMalloc(&c->probe, (size_t)capacity * 16));
-    CK(cudaMemsetAsync(c->probe, 0, (size_t)capacity * 16, c->stream));
+    CK(cudaHostAlloc((void **)&c->probe, (size_t)capacity * 16, cudaHostAllocMapped));
+    memset(c->probe, 0, (size_t)capacity * 16);
+    *c->progress = c->t;
     c->px = x;
     c->py = y;
     c->probe_cap = capacity;
@@ -2158,12 +2180,21 @@ extern "C" int lbm_probe_read(lbm_ctx *c, int64_t t0, int n, double *uxuy)
         return fail(LBM_ERR_ARG, "lbm_probe_read: steps [%lld, %lld) not in the ring (time %lld, capacity %d)", (long long)t0,
                     (long long)t0 + n, c->t, c->probe_cap);
     CK(cudaSetDevice(c->device));
-    CK(cudaStreamSynchronize(c->stream_edge));
-    CK(cudaStreamSynchronize(c->stream));
+    // Wait for the newest requested sample only: the device may be many steps further down its queue. (When both
+    // streams have drained, everything that was ever going to be recorded is in the ring.)
+    const long long target = t0 + n - 1;
+    volatile long long *progress = c->progress;
+    while (*progress < target) {
+        const cudaError_t a = cudaStreamQuery(c->stream_edge), b = cudaStreamQuery(c->stream);
+        if (a != cudaSuccess && a != cudaErrorNotReady) CK(a);
+        if (b != cudaSuccess && b != cudaErrorNotReady) CK(b);
+        if (a == cudaSuccess && b == cudaSuccess) break;
+    }
+    __sync_synchronize();
     for (int i = 0; i < n;) {
         const int slot = (int)((t0 + i) % c->probe_cap);
         const int run = std::min(n - i, c->probe_cap - slot);
-        CK(cudaMemcpy(uxuy + 2 * i, c->probe + 2 * slot, (size_t)run * 16, cudaMemcpyDeviceToHost));
+        memcpy(uxuy + 2 * i, c->probe + 2 * slot, (size_t)run * 16);
         i += run;
     }
     return LBM_OK;
