@@ -30,13 +30,25 @@ EPS, OMEGA = 0.01, 1.0
 
 
 # stdout carries exactly ONE line, the JSON result: everything else that writes to file descriptor 1 while the
-# bench runs (NCCL's version banner, library chatter) is sent to stderr.
-_REAL_STDOUT = os.dup(1)
-os.dup2(2, 1)
+# bench runs (NCCL's version banner, library chatter) is sent to stderr. Done by main(), not at import.
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
 
 
 def emit(line):
-    os.write(_REAL_STDOUT, (json.dumps(line) + '\n').encode())
+    text = (json.dumps(line) + '\n').encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(text.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, text)
 
 
 def measured_peak_gbs():
@@ -266,6 +278,7 @@ def main():
                          'lattice (single GPU; evidence for the flag-mask vs edge-kernel choice)')
     ap.add_argument('--bc-mode', default='auto', choices=['auto', 'mask', 'edge'])
     args = ap.parse_args()
+    claim_stdout()
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))

@@ -280,6 +280,7 @@ def test_cpu_baseline_processes_equal_one_process():
     line = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '2', '--warmup',
                            '1', '--cpu-size', '256'], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert line.returncode == 0, line.stderr[-2000:]
+    assert len(line.stdout.strip().splitlines()) == 1, 'bench.py must print exactly one line on stdout'
     d = json.loads(line.stdout.strip().splitlines()[-1])
     assert d['impl'] == 'reference' and d['value'] > 0 and d['cpu_baseline']['kind'] == 'port' and d['e2e']['value'] == d['value']
 
