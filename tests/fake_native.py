@@ -19,7 +19,9 @@ class _Ctx:
         self.t = 0
         self.launches = 0
         self.steps_log = []      # omegas, for assertions
-        self.calls = []          # ('step', n) / ('fields', 1) in call order
+        self.calls = []          # ('step', n) / ('fields', 1) / ('probe_config', x, y) / ('probe_read', t0, n) in call order
+        self.probe = None        # (x, y, capacity, t_config)
+        self.samples = {}        # t -> (ux, uy)
 
 
 class FakeLib:
@@ -72,6 +74,7 @@ class FakeLib:
         c = self._c(ctx)
         c.state = (np.array(_arr(f, (c.nx, c.ny, 9))), np.array(_arr(rho, (c.nx, c.ny))), np.array(_arr(u, (c.nx, c.ny, 2))))
         c.t = 0
+        c.samples = {}
         return 0
 
     def lbm_step(self, ctx, omega, n):
@@ -85,6 +88,8 @@ class FakeLib:
             c.t += 1
             c.launches += 1
             c.steps_log.append(omega)
+            if c.probe is not None:
+                c.samples[c.t] = np.array(c.state[2][c.probe[0], c.probe[1]])
         return 0
 
     def lbm_materialize_region(self, ctx, x0, x1, y0, y1, f, rho, u):
@@ -97,6 +102,21 @@ class FakeLib:
         for ptr, src, tail in ((f, c.state[0], (9,)), (rho, c.state[1], ()), (u, c.state[2], (2,))):
             if ptr:
                 _arr(ptr, (x1 - x0, y1 - y0) + tail)[...] = src[x0:x1, y0:y1]
+        return 0
+
+    def lbm_probe_config(self, ctx, x, y, capacity):
+        c = self._c(ctx)
+        c.probe, c.samples = (x, y, capacity, c.t), {}
+        c.calls.append(('probe_config', x, y))
+        return 0
+
+    def lbm_probe_read(self, ctx, t0, n, out):
+        c = self._c(ctx)
+        if c.probe is None or t0 < 1 or t0 + n - 1 > c.t or c.t - t0 >= c.probe[2] or any(t not in c.samples for t in range(t0, t0 + n)):
+            self.err = b'lbm_probe_read: steps not in the ring'
+            return 1
+        c.calls.append(('probe_read', t0, n))
+        _arr(out, (n, 2))[...] = [c.samples[t] for t in range(t0, t0 + n)]
         return 0
 
     def lbm_minmax(self, ctx, x0, x1, y0, y1, out):

@@ -100,6 +100,52 @@ def test_cell_reads_extrema_and_ndarray_behaviour(L):
         np.asarray(rho)[0, 0] = 1.0                                      # cached results are read-only views
 
 
+def test_per_step_cell_reads_move_to_the_probe_ring(L):
+    """experiments.py:703-704 reads velocity[px, py] after EVERY step: the second such read configures the probe on
+    that cell, later reads are served from the ring (no materialisation launch); other cells, other fields, a jump
+    in time and a fresh upload fall back to the region read."""
+    f, rho, u = start(seed=7)
+    ref = (f, rho, u)
+    lat = None
+    for t in range(1, 9):
+        f, rho, u = L.lattice_boltzmann_step(f, rho, u, 1.3)
+        ref = onp.step(*ref, 1.3)
+        assert np.array_equal(np.array(u[4, 5, ...]), ref[2][4, 5])
+        assert u[4, 5, 1] == ref[2][4, 5, 1] and rho[4, 5] == ref[1][4, 5]
+        lat = next(iter(L._lattices.values()))[0]
+        calls = L.fake._c(lat._ctx).calls
+        if t == 2:
+            assert ('probe_config', 4, 5) in calls
+        if t >= 3:
+            assert calls[-3][0] == 'probe_read' and calls[-2][0] == 'probe_read' and calls[-1] == ('fields', 1)   # u, u, rho
+    assert np.array_equal(np.array(u[2, 3]), ref[2][2, 3])               # another cell: region read, the probe stays
+    assert lat._probe[:2] == (4, 5)
+    for _ in range(3):                                                   # three steps without a read: the ring has them all
+        f, rho, u = L.lattice_boltzmann_step(f, rho, u, 1.3)
+        ref = onp.step(*ref, 1.3)
+    assert np.array_equal(np.array(u[4, 5]), ref[2][4, 5])
+    f, rho, u = L.lattice_boltzmann_step(np.asarray(f), np.asarray(rho), np.asarray(u), 1.3)   # fresh upload
+    ref = onp.step(*ref, 1.3)
+    assert np.array_equal(np.array(u[4, 5]), ref[2][4, 5])
+
+
+def test_a_probe_the_caller_configured_is_used_and_kept(L):
+    from lattice_boltzmann_parallel_solver_b200.engine import Lattice
+    f, rho, u = start(seed=8)
+    lat = Lattice(12, 10)
+    lat.probe(3, 3, capacity=16)
+    lat.load(f, rho, u, 1.0)
+    ref = (f, rho, u)
+    for t in range(1, 5):
+        hs = lat.request_step(1.0)
+        ref = onp.step(*ref, 1.0)
+        assert np.array_equal(np.array(hs[2][3, 3]), ref[2][3, 3])       # on the probe cell: from the ring
+        assert np.array_equal(np.array(hs[2][6, 2]), ref[2][6, 2])       # elsewhere: region reads, no re-configuration
+    calls = L.fake._c(lat._ctx).calls
+    assert [c for c in calls if c[0] == 'probe_config'] == [('probe_config', 3, 3)]
+    assert sum(1 for c in calls if c[0] == 'probe_read') == 4
+
+
 def test_modified_result_forces_a_fresh_upload(L):
     f, rho, u = start(seed=4)
     f, rho, u = L.lattice_boltzmann_step(f, rho, u, 1.0)
