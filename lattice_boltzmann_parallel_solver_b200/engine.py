@@ -14,6 +14,11 @@ DEFERRED: a call only queues its step (up to `MAX_DEFERRED`, same omega) and han
 time; the queue is launched when somebody looks at a result, when it is full, or when omega changes. By then the
 loop has dropped the old handles, and a whole batch goes to `lbm_step(n)` at once — which is what lets the
 reference's own driver loops run on the two-steps-per-pass kernel and on CUDA-graph replay.
+
+Drivers that look at ONE velocity cell after every step (`vel_at_p.append(np.linalg.norm(velocity[px, py, ...]))`,
+experiments.py:703-704) cannot defer anything; for them the second consecutive read of the same cell configures the
+device-side probe on it (`Lattice._probe_sample`), after which a read costs one step launch and a 16-byte copy out
+of the host-mapped probe ring.
 """
 import weakref
 
