@@ -237,22 +237,101 @@ def run_reference(args, rank):
         'impl': 'reference', 'metric': 'D2Q9 fp64 MLUPS', 'value': mlups, 'unit': 'MLUPS', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': workload_config(args, 1),
+        'config': {'workload': f'{n}x{n} periodic shear-wave lattice on the host cores (a bounded sample of the GPU arm\'s '
+                               f'workload, which is {args.size}x{args.size} per GPU: MLUPS is size-normalised, the numpy path '
+                               f'needs ~400 B/cell so the full size neither fits nor finishes)',
+                   'lattice': [n, n], 'gpu_arm_lattice_per_gpu': [args.size, args.size], 'omega': OMEGA, 'epsilon': EPS,
+                   'decomposition': f'{k} processes x 1 thread, slabs along the slow axis with a ghost ring'},
         'cpu_baseline': {'value': mlups, 'unit': 'MLUPS', 'cores': k, 'kind': 'port', 'sample': sample},
         'e2e': {'value': mlups, 'unit': 'MLUPS', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     emit(line)
 
 
-def workload_config(args, world):
+def workload_config(args, world, depth=3):
     if args.strong:
         wl = f'strong scaling: {args.size}x{args.size} total periodic shear-wave lattice over {world} GPU(s)'
     else:
         wl = f'weak scaling: {args.size}x{args.size} periodic shear-wave lattice per GPU ({args.size * world}x{args.size} total)'
     return {'workload': wl, 'lattice_per_gpu': [args.size // world if args.strong else args.size, args.size],
-            'omega': OMEGA, 'epsilon': EPS, 'decomposition': f'{world}x1 slabs along the slow axis, 2 ghost rows each side'
+            'omega': OMEGA, 'epsilon': EPS, 'time_steps_per_pass': depth,
+            'decomposition': f'{world}x1 slabs along the slow axis, {max(depth, 2)} ghost rows each side'
             if world > 1 else 'single block, periodic wrap in-kernel',
             'l2': 'populations are 19.3 GB per GPU per buffer >> 126 MB L2; no flush needed'}
+
+
+def source_sha():
+    """sha256 of the kernel sources: profiles/traffic.json is only quoted for the binary it was captured on."""
+    import hashlib
+    h = hashlib.sha256()
+    for name in ('lbm_b200.cu', 'lbm_device.cuh'):
+        with open(os.path.join(ROOT, 'lattice_boltzmann_parallel_solver_b200', 'csrc', name), 'rb') as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def measured_traffic(key):
+    """DRAM bytes per launch from the committed ncu capture, or None when the kernels changed since it was taken."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as fh:
+            tj = json.load(fh)
+    except Exception:
+        return None, 'profiles/traffic.json missing'
+    if tj.get('source_sha256') != source_sha():
+        return None, 'profiles/traffic.json was captured on other kernel sources (sha mismatch): re-run profiles/run_profiles.sh'
+    return tj.get(key), tj.get(key + '_source')
+
+
+PARITY_PERIOD = 64
+
+
+def run_parity(lat, world, rank, nx_local, ny, prof, steps, barrier, all_sum, all_max):
+    """Values, not just completion, of the decomposition the timed run uses (outside the timed region): the lattice is
+    loaded with a density that varies ALONG the slab axis — rho(x) with period 64 in the GLOBAL row index — on top of
+    the shear wave u_x(y), and advanced `steps` steps through the same launches as the timed run (multi-step passes,
+    ghost-row stores over NVLink, flag handshake, edge/interior overlap). The global solution is then periodic in x
+    with period 64, i.e. equal to a 64 x ny periodic lattice, which the C oracle (the checker: oracle/lbm_oracle.c,
+    pinned to the reference bit for bit) runs in a second. Every rank compares its first and last four interior rows —
+    the rows that straddle the slab boundaries and depend on the neighbours' ghost stores — and four rows in the
+    middle, all populations, density and velocity, bit for bit."""
+    from oracle import lbm_c, lbm_numpy as onp
+    g = lat.ghost[0]
+    NX = nx_local + 2 * g
+    tab = 1.0 + 0.02 * np.sin(np.divide(2 * np.pi * np.arange(PARITY_PERIOD), PARITY_PERIOD))
+    X = (rank * nx_local + np.arange(NX) - g) % (nx_local * world)      # global row of every local row, ghosts included
+    lat.load_equilibrium(OMEGA, rho_x=tab[X % PARITY_PERIOD], ux_y=prof)
+    barrier()
+    lat.run(steps)
+    lat.sync()
+    rho = np.repeat(tab[:, None], ny, axis=1)
+    u = np.zeros((PARITY_PERIOD, ny, 2))
+    u[..., 0] = prof[None, :]
+    ref = lbm_c.run(onp.equilibrium(rho, u), rho, u, OMEGA, lbm_c.periodic(), steps)
+    mism, maxd, rows = 0, 0.0, 0
+    for r0 in sorted({g, g + (nx_local // 2 // 4) * 4, NX - g - 4}):
+        got = lat.fields(region=(r0, r0 + 4, 0, ny))
+        idx = X[r0:r0 + 4] % PARITY_PERIOD
+        for a, b in zip(got, ref):
+            b = b[idx]
+            mism += int(np.count_nonzero(a != b))
+            maxd = max(maxd, float(np.max(np.abs(a - b))))
+        rows += 4
+    barrier()
+    return {'checked': True, 'mismatches': int(all_sum(mism)), 'max_abs_diff': float(all_max(maxd)),
+            'rows': int(all_sum(rows)), 'values_compared': int(all_sum(rows)) * ny * 12, 'steps': steps,
+            'field': f'rho(x) = 1 + 0.02 sin(2 pi (x mod {PARITY_PERIOD}) / {PARITY_PERIOD}) in the global row index (varies along '
+                     f'the slab axis), u_x(y) = the shear wave; oracle: {PARITY_PERIOD} x {ny} periodic lattice, C restatement',
+            'rows_per_rank': 'first 4 and last 4 interior rows (next to the neighbours\' ghost rows) + 4 mid rows; f, density, velocity'}
+
+
+def timed_steps(lat, stream, n, reduce_max):
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    lat.run(n)
+    e1.record(stream)
+    lat.sync()
+    return reduce_max(e0.elapsed_time(e1))
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -277,6 +356,10 @@ def main():
                     help='shear: the headline periodic lattice; karman: inlet/outlet/plate rule set scaled to the same '
                          'lattice (single GPU; evidence for the flag-mask vs edge-kernel choice)')
     ap.add_argument('--bc-mode', default='auto', choices=['auto', 'mask', 'edge'])
+    ap.add_argument('--depth', type=int, default=3, choices=[2, 3, 4], help='time steps per pass of the multi-step kernel')
+    ap.add_argument('--no-parity', action='store_true', help='skip the x-periodic parity job against the C oracle')
+    ap.add_argument('--parity-steps', type=int, default=13)
+    ap.add_argument('--no-sub', action='store_true', help='skip the strong-scaling and von Karman sub-records')
     args = ap.parse_args()
     claim_stdout()
 
@@ -300,129 +383,188 @@ def main():
         ldist.ensure_process_group('nccl')
     assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}'
 
-    ny = args.size
-    nx_local = args.size // world if args.strong else args.size
-    nx_global = nx_local * world
-    prof = EPS * np.sin(np.divide(2 * np.pi * np.arange(ny), ny))   # initial_values.py:83-88
-
     def barrier():
         if world > 1:
             dist.barrier()
 
-    if args.workload == 'karman':
-        assert world == 1, 'the BC-bearing comparison is a single-GPU measurement'
-        lat = karman_lattice(nx_local, ny, {'auto': N.BC_AUTO, 'mask': N.BC_MASK, 'edge': N.BC_EDGE}[args.bc_mode])
-        args.no_e2e = True
-    elif world == 1:
-        lat = Lattice(nx_local, ny)
-    else:
-        # two ghost rows per side: the two-steps-per-pass kernel needs the depth-2 dependency cone of its edge rows
-        lat = Lattice(nx_local + 4, ny, ghost=(2, 0))
-        cart = ldist.comm_world().Create_cart(dims=[world, 1], periods=[True, True])
-        par.communication(cart).attach(lat)
-    if args.workload == 'karman':
-        lat.load_equilibrium(float(np.reciprocal(3 * 0.04 + 0.5)), rho0=1.0, ux0=0.1)
-    else:
-        lat.load_equilibrium(OMEGA, ux_y=prof)
-    if args.single_step:
-        lat.set_option('fused', 0)
-    barrier()
+    def reduce(v, op):
+        if world == 1:
+            return v
+        t = torch.tensor([float(v)], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=op)
+        return float(t.item())
 
-    stream = torch.cuda.ExternalStream(lat.stream)
-    lat.run(args.warmup)
-    lat.sync()
-    barrier()
-    l0 = lat.launches
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    barrier()
-    e0.record(stream)
-    lat.run(args.steps)
-    e1.record(stream)
-    lat.sync()
-    torch.cuda.synchronize()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
-    launches = lat.launches - l0
-    if world > 1:
-        t = torch.tensor([ms], device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    cells_total = nx_global * ny
-    mlups = cells_total * args.steps / (ms * 1e-3) / 1e6
+    def all_max(v):
+        return reduce(v, dist.ReduceOp.MAX)
+
+    def all_sum(v):
+        return reduce(v, dist.ReduceOp.SUM)
+
+    peak, peak_src = measured_peak_gbs()
+    depth = 1 if args.single_step else args.depth
+    bc_mode = {'auto': N.BC_AUTO, 'mask': N.BC_MASK, 'edge': N.BC_EDGE}[args.bc_mode]
+
+    def make_lattice(workload, strong, size):
+        """The device lattice of one measurement: (lattice, nx_local, ny, profile)."""
+        ny = size
+        nx_local = size // world if strong else size
+        prof = EPS * np.sin(np.divide(2 * np.pi * np.arange(ny), ny))   # initial_values.py:83-88
+        if workload == 'karman':
+            assert world == 1, 'the BC-bearing workload is a single-GPU measurement'
+            lat = karman_lattice(nx_local, ny, bc_mode)
+        elif world == 1:
+            lat = Lattice(nx_local, ny)
+        else:
+            # `depth` ghost rows per side: the dependency cone of a multi-step pass over the slab's edge rows; the
+            # neighbour's edge launch stores them over NVLink, one exchange and one flag handshake per pass
+            g = max(depth, 2)
+            lat = Lattice(nx_local + 2 * g, ny, ghost=(g, 0))
+            cart = ldist.comm_world().Create_cart(dims=[world, 1], periods=[True, True])
+            par.communication(cart).attach(lat)
+        if depth == 1:
+            lat.set_option('fused', 0)
+        elif workload != 'karman':
+            lat.set_option('fused_depth', depth)
+        return lat, nx_local, ny, prof
+
+    def load(lat, workload, prof):
+        if workload == 'karman':
+            lat.load_equilibrium(float(np.reciprocal(3 * 0.04 + 0.5)), rho0=1.0, ux0=0.1)
+        else:
+            lat.load_equilibrium(OMEGA, ux_y=prof)
+        barrier()
+
+    def measure(lat, nx_local, ny, steps, warmup, sample_clocks):
+        """`warmup` untimed steps, then exactly `steps` steps between CUDA events on the library's stream, bracketed by
+        barrier + synchronize; max over ranks."""
+        stream = torch.cuda.ExternalStream(lat.stream)
+        lat.run(warmup)
+        lat.sync()
+        barrier()
+        l0 = lat.launches
+        sampler = ClockSampler(local) if sample_clocks and rank == 0 else None
+        if sampler:
+            sampler.start()
+        torch.cuda.synchronize()
+        barrier()
+        ms = timed_steps(lat, stream, steps, all_max)
+        torch.cuda.synchronize()
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        cells_total = nx_local * world * ny
+        return {'ms': ms, 'mlups': cells_total * steps / (ms * 1e-3) / 1e6, 'launches': lat.launches - l0, 'clocks': clocks,
+                'stream': stream}
+
+    # ---- headline ----------------------------------------------------------------------------------------------
+    lat, nx_local, ny, prof = make_lattice(args.workload, args.strong, args.size)
+    parity = None
+    if args.workload == 'shear' and not args.no_parity:
+        parity = run_parity(lat, world, rank, nx_local, ny, prof, args.parity_steps, barrier, all_sum, all_max)
+    load(lat, args.workload, prof)
+    head = measure(lat, nx_local, ny, args.steps, args.warmup, True)
+    ms, mlups, launches, clocks, stream = head['ms'], head['mlups'], head['launches'], head['clocks'], head['stream']
+    per_gpu_cells = nx_local * ny
+    cells_total = per_gpu_cells * world
 
     # ---- roofline ---------------------------------------------------------------------------------------------
-    # Dominant kernel of the timed region: k_step2x, which advances TWO time steps per launch (temporal blocking).
-    # achieved = algorithmic bytes per launch (2 steps x 144 B x cells) / mean launch time (CUDA events above; the
-    # region is `pairs` two-step launches + 1-2 one-step launches, all back to back on one stream).
-    peak, peak_src = measured_peak_gbs()
-    per_gpu_cells = nx_local * ny
-    fused = not args.single_step
-    step_ms = ms / args.steps
+    # Dominant kernel: the multi-step pass (k_stepNx<depth>: `depth` time steps per launch). Its launch duration is
+    # measured live, alone: `fused_exact` makes lbm_step(n) exactly n / depth passes (CUDA events on the library's
+    # stream, same lattice, right after the timed region). achieved = algorithmic bytes per launch (depth x 144 B x
+    # cells) / that duration; dram_frac = measured DRAM traffic of one launch (ncu, profiles/traffic.json) / duration
+    # / peak — the fraction of the memory roof the kernel really uses.
+    fused = depth > 1
     if fused:
-        algo_launch = 2 * per_gpu_cells * ALGO_BYTES_PER_UPDATE
-        achieved = algo_launch / (2 * step_ms * 1e-3) / 1e9
-        kernel = ('k_step2x<128> (two time steps per launch: two columns per thread, shared-memory ring of the '
-                  'intermediate rows)')
+        spl = depth if args.workload != 'karman' else 2
+        lat.set_option('fused_exact', 1)
+        n_pure = spl * max(4, min(24, args.steps // spl))
+        lat.run(spl * 2)
+        lat.sync()
+        barrier()
+        ms_pure = timed_steps(lat, stream, n_pure, all_max)
+        lat.set_option('fused_exact', 0)
+        launch_ms = ms_pure / (n_pure // spl)
+        algo_launch = spl * per_gpu_cells * ALGO_BYTES_PER_UPDATE
+        kernel = (f'k_stepNx<128,{depth}> ({depth} time steps per launch: two columns per thread, {depth - 1} shared-memory '
+                  f'ring(s) of intermediate rows)')
+        tkey = f'k_stepNx{depth}_dram_bytes_per_launch_16384'
         if args.workload == 'karman':
-            kernel += (' on the rows whose two-step dependency cone is all fluid + two one-step mask launches through '
-                       'a window on each strip of boundary rows (inlet/outlet rows, plate rows)')
+            kernel = ('k_step2x<128> on the rows whose two-step dependency cone is all fluid + two one-step mask launches '
+                      'through a window on each strip of boundary rows (inlet/outlet rows, plate rows); duration = one pass')
+            tkey = 'k_step2x_dram_bytes_per_launch_16384'
     else:
+        launch_ms = ms / args.steps
         algo_launch = per_gpu_cells * ALGO_BYTES_PER_UPDATE
-        achieved = algo_launch / (step_ms * 1e-3) / 1e9
         kernel = 'k_step_pair (one time step per launch, two cells per thread)'
+        tkey = 'dram_bytes_per_launch_16384'
+        spl = 1
+    achieved = algo_launch / (launch_ms * 1e-3) / 1e9
+    at_capture_size = args.size == 16384 and not args.strong
+    traffic, traffic_src = measured_traffic(tkey) if at_capture_size else (None, 'captured at 16384^2 per GPU only')
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': None, 'peak_source': peak_src, 'kernel': kernel,
-                'algorithmic_bytes_per_launch': algo_launch, 'steps_per_launch': 2 if fused else 1,
+                'traffic': traffic, 'traffic_source': traffic_src,
+                'dram_frac': (traffic / (launch_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                'peak_source': peak_src, 'kernel': kernel, 'launch_ms': launch_ms,
+                'algorithmic_bytes_per_launch': algo_launch, 'steps_per_launch': spl,
+                'mlups_of_the_kernel_alone': per_gpu_cells * world * spl / (launch_ms * 1e-3) / 1e6,
                 'mlups_at_peak_one_step_per_launch': peak * 1e9 / ALGO_BYTES_PER_UPDATE / 1e6,
                 'frac_of_nominal_8TBps': achieved / 8000.0}
-    prof_path = os.path.join(ROOT, 'profiles', 'traffic.json')
-    if os.path.exists(prof_path):
-        try:
-            with open(prof_path) as fh:
-                tj = json.load(fh)
-            roofline['traffic'] = tj.get('k_step2x_dram_bytes_per_launch_16384' if fused else 'dram_bytes_per_launch_16384')
-            if fused:
-                roofline['note'] = ('frac > 1 by construction: the kernel moves ~half the algorithmic bytes of its two '
-                                    'steps through DRAM (traffic vs algorithmic_bytes_per_launch); it is issue/latency '
-                                    'bound, not bandwidth bound. The one-step kernel the north star describes is timed '
-                                    'below (single_step).')
-        except Exception:
-            pass
-    # the one-step-per-launch kernel (the north star's "reads each population once and writes it once"), timed
-    # live in the same process for the same lattice
     if fused:
+        roofline['note'] = (f'frac > 1 by construction: a {spl}-step pass moves ~1/{spl} of the algorithmic bytes of its steps '
+                            'through DRAM (traffic vs algorithmic_bytes_per_launch; dram_frac is the share of the memory '
+                            'roof it really uses); it is fp64-issue/latency bound. The one-step kernel the north star '
+                            'describes is timed below (single_step).')
+        # the one-step-per-launch kernel (the north star's "reads each population once and writes it once"), timed
+        # live in the same process on the same lattice
         lat.set_option('fused', 0)
         k1 = max(10, args.steps // 4)
         lat.run(3)
         lat.sync()
         barrier()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record(stream)
-        lat.run(k1)
-        s1.record(stream)
-        lat.sync()
-        ms1 = s0.elapsed_time(s1)
-        if world > 1:
-            t = torch.tensor([ms1], device='cuda')
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms1 = float(t.item())
+        ms1 = timed_steps(lat, stream, k1, all_max)
         a1 = per_gpu_cells * ALGO_BYTES_PER_UPDATE / (ms1 / k1 * 1e-3) / 1e9
-        roofline['single_step'] = {'kernel': 'k_step_pair' + (' + edge-list kernel' if args.workload == 'karman' else ''), 'steps': k1, 'ms_per_step': ms1 / k1,
-                                   'mlups': cells_total * k1 / (ms1 * 1e-3) / 1e6, 'achieved': a1, 'frac': a1 / peak,
-                                   'frac_of_nominal_8TBps': a1 / 8000.0,
-                                   'traffic': tj.get('dram_bytes_per_launch_16384') if os.path.exists(prof_path) else None}
+        t1, _ = measured_traffic('dram_bytes_per_launch_16384') if at_capture_size else (None, None)
+        roofline['single_step'] = {'kernel': 'k_step_pair' + (' + edge-list kernel' if args.workload == 'karman' else ''),
+                                   'steps': k1, 'ms_per_step': ms1 / k1, 'mlups': cells_total * k1 / (ms1 * 1e-3) / 1e6,
+                                   'achieved': a1, 'frac': a1 / peak, 'frac_of_nominal_8TBps': a1 / 8000.0, 'traffic': t1,
+                                   'dram_frac': (t1 / (ms1 / k1 * 1e-3) / 1e9 / peak) if t1 else None}
         lat.set_option('fused', 1)
 
     # ---- e2e: the whole job through the reference-shaped API with HOST buffers ------------------------------
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and args.workload == 'shear':
         e2e = run_e2e(args, lat, world, rank, nx_local, ny, prof, barrier)
     lat.close()
+    del lat
+
+    # ---- sub-records: BASELINE.json config 5 in full (strong scaling 32768^2 at this N) and the BC-bearing case ----
+    def sub_record(workload, strong, size, steps, warmup):
+        try:
+            l2, nxl, ny2, prof2 = make_lattice(workload, strong, size)
+        except MemoryError as e:
+            return {'skipped': str(e)[:160]}
+        par2 = None
+        if workload == 'shear' and not args.no_parity:
+            par2 = run_parity(l2, world, rank, nxl, ny2, prof2, args.parity_steps, barrier, all_sum, all_max)
+        load(l2, workload, prof2)
+        m = measure(l2, nxl, ny2, steps, warmup, False)
+        l2.close()
+        rec = {'value': m['mlups'], 'unit': 'MLUPS', 'ms_per_step': m['ms'] / steps, 'steps': steps, 'warmup': warmup,
+               'gpu_launches': int(m['launches']), 'n_gpus': world, 'lattice_per_gpu': [nxl, ny2], 'lattice_total': [nxl * world, ny2]}
+        if par2 is not None:
+            rec['parity'] = par2
+        return rec
+
+    strong_rec = karman_rec = None
+    if args.workload == 'shear' and not args.strong and not args.no_sub:
+        ssteps = max(depth * 4, min(args.steps, 60))
+        strong_rec = sub_record('shear', True, 32768, ssteps, max(3, min(args.warmup, 12)))
+        strong_rec['scaling'] = 'strong'
+        strong_rec['workload'] = f'strong scaling: 32768x32768 total periodic shear-wave lattice over {world} GPU(s) (BASELINE.json configs[4])'
+        if world == 1:
+            karman_rec = sub_record('karman', False, args.size, max(8, min(args.steps, 60)), max(3, min(args.warmup, 12)))
+            karman_rec['workload'] = (f'von Karman rule set (inlet row, outlet rows, plate of ny/4.5 at nx/4; nu 0.04, u_in 0.1) on '
+                                      f'{args.size}x{args.size}: the BC-bearing case of SURVEY.md section 8(d)')
+            karman_rec['vs_periodic'] = karman_rec['value'] / mlups if 'value' in karman_rec else None
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:   # CPU baseline: rank 0 at N=1 only
@@ -443,12 +585,17 @@ def main():
     if rank == 0 and world == 1 and not args.no_ref_config and args.workload == 'shear':
         ref_cfg = reference_scaling_test()
     if rank == 0:
+        cfg = workload_config(args, world, depth)
+        if args.workload == 'karman':
+            cfg.update({'workload': f'von Karman rule set (inlet, outlet, plate) on {args.size}x{args.size}, bc_mode={args.bc_mode}',
+                        'omega': float(np.reciprocal(3 * 0.04 + 0.5)), 'epsilon': None})
         line = {
             'metric': 'D2Q9 fp64 MLUPS', 'value': mlups, 'unit': 'MLUPS', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
             'scaling': 'strong' if args.strong else 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': dict(workload_config(args, world), **({'workload': f'von Karman rule set (inlet, outlet, plate) on {args.size}x{args.size}, bc_mode={args.bc_mode}', 'omega': float(np.reciprocal(3 * 0.04 + 0.5)), 'epsilon': None} if args.workload == 'karman' else {})), 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
-            'roofline': roofline, 'cpu_baseline': cpu, 'reference_scaling_test': ref_cfg,
+            'config': cfg, 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'parity': parity,
+            'roofline': roofline, 'cpu_baseline': cpu, 'strong': strong_rec, 'karman': karman_rec,
+            'reference_scaling_test': ref_cfg,
         }
         emit(line)
     if world > 1:

@@ -87,11 +87,13 @@ typedef struct {
 } lbm_bc_desc;
 
 /* Test hook: compares the kernels' hand-expanded fp64 division (shared reciprocal, lbm_device.cuh) and square root
- * with the compiler's IEEE __ddiv_rn / __dsqrt_rn on n generated operand pairs. out[0], out[1] = number of
- * quotients / roots whose bits differ (must be 0), out[2..3] = operands of the first differing quotient,
- * out[4] = operand of the first differing root. Guards the bit-exactness of compute_velocity_field
+ * — both the variants that call the library for unusual operands and the branch-free ones of the multi-step kernels,
+ * which only flag such operands — with the compiler's IEEE __ddiv_rn / __dsqrt_rn on n generated operand pairs.
+ * out[0], out[1] = number of quotients / roots whose bits differ (must be 0), out[2..3] = operands of the first
+ * differing quotient, out[4] = operand of the first differing root, out[5], out[6] = how many quotients / roots the
+ * branch-free variants answered themselves (not flagged). Guards the bit-exactness of compute_velocity_field
  * (src/lattice_boltzmann_method.py:122-133) and of the norm in equilibrium_distr_func (:185). */
-int lbm_selftest_arith(int device, int64_t n, uint64_t seed, uint64_t out[5]);
+int lbm_selftest_arith(int device, int64_t n, uint64_t seed, uint64_t out[7]);
 
 /* Test hook, host only (no CUDA call): the row plan of the two-steps-per-pass schedule on a lattice with boundary
  * cells. row_has_boundary[x] != 0 marks rows that hold a non-fluid cell. Out: strips[2i], strips[2i+1] = rows [a, b)

@@ -145,6 +145,20 @@ class KindMap:
     def is_trivial(self):
         return not self.map.any()
 
+    def digest(self):
+        """Content hash of the compiled description (kind bytes + kind table + K / constant rows): two bundles that
+        compile to the same bytes are the same scenario for the device (lattice cache key)."""
+        import hashlib
+        t = self.table
+        h = hashlib.sha256()
+        h.update(repr(self.shape).encode())
+        h.update(np.ascontiguousarray(self.map).tobytes())
+        h.update(repr(t.kinds).encode())
+        h.update(np.array(t.k_rows, dtype=np.float64).tobytes())
+        h.update(np.array(t.c_rows, dtype=np.float64).tobytes())
+        h.update(np.array([t.rho_in, t.rho_out], dtype=np.float64).tobytes())
+        return h.hexdigest()
+
 
 class _KindView:
     """A rectangular window of a KindMap (the reference applies inlet/outlet to f_post[1:-1, 1:-1],

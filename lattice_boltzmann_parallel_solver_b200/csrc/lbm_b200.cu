@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -79,8 +80,10 @@ struct StepParams {
     int bpr;           // blocks per row
     int seg, nb;       // k_step2x: output rows per block; length of the second row range
     int pf;            // k_step2x: rows ahead of the march whose source segments are prefetched into L2 (0 = off)
+    int strip0;        // k_stepNx: index of the first column strip of this launch (materialising a sub-rectangle)
     int y0, y1;        // columns handled: [y0, y1)
     double omega;
+    double omega_last; // k_stepNx: omega of the LAST level's collision (differs when the caller changed omega)
     const uint8_t *kind_map;   // [x*pitch + y] or null
     const lbm_kind *kinds;
     const double *ktab, *ctab;
@@ -111,6 +114,7 @@ struct StepParams {
     long long timeout_cycles;
     unsigned *done_counter;         // last-block-done counter
     unsigned *err_flag;
+    unsigned *err_host;             // host-mapped mirror of err_flag
     int n_blocks;
 };
 
@@ -297,24 +301,34 @@ __device__ __forceinline__ void store_halo(const StepParams &P, int x, int y, co
 // cross-GPU ordering: wait until every remote neighbour has published `wait_value`, publish `signal_value`
 // once the whole grid has finished its (peer) stores.
 // -------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void halo_wait(const StepParams &P)
+__device__ __forceinline__ bool halo_wait(const StepParams &P)
 {
-    if (P.wait_value == 0) return;
+    if (P.wait_value == 0) return true;
+    __shared__ int halo_ok;
     if (threadIdx.x == 0) {
+        // Sticky: once a wait has timed out on this context every later ghost-touching kernel gives up at once — it
+        // neither computes from stale ghosts nor stores or publishes anything, so the neighbours time out as well
+        // instead of consuming wrong values, and the host reports LBM_ERR_TIMEOUT from its next call.
+        int ok = *(volatile unsigned *)P.err_flag == 0;
         const long long t0 = clock64();
-        for (int s = 0; s < 9; s++) {
+        for (int s = 0; s < 9 && ok; s++) {
             if (!P.flag_out[s]) continue;   // not a remote neighbour
             while ((int)(P.flag_in[s] - P.wait_value) < 0) {
                 if (clock64() - t0 > P.timeout_cycles) {   // a peer is not stepping in lockstep
-                    atomicExch(P.err_flag, 0x80000000u | (P.wait_value << 8) | (unsigned)s);   // who waited for what
+                    const unsigned code = 0x80000000u | (P.wait_value << 8) | (unsigned)s;   // who waited for what
+                    atomicCAS(P.err_flag, 0u, code);
+                    *(volatile unsigned *)P.err_host = code;   // host-mapped mirror: the host sees it without a CUDA call
+                    ok = 0;
                     break;
                 }
                 __nanosleep(200);
             }
         }
         __threadfence_system();
+        halo_ok = ok;
     }
     __syncthreads();
+    return halo_ok != 0;
 }
 
 __device__ __forceinline__ void halo_signal(const StepParams &P)
@@ -469,7 +483,7 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepParams
         if (kind) k = P.kinds[kind];
     }
     pdl_wait();
-    if (HALO && !FINAL) halo_wait(P);
+    if (HALO && !FINAL && !halo_wait(P)) return;
     if (active) step_cell<HALO, FINAL>(P, x, y, kind, k);
     if (HALO && !FINAL) halo_signal(P);
 }
@@ -563,7 +577,7 @@ template <int T, bool HALO, bool PROBE>
 __global__ void __launch_bounds__(T, 4) k_step2x(const __grid_constant__ StepParams P)
 {
     extern __shared__ double ring[];   // [4 slots][6 populations: 2,4,5,6,7,8][2T columns]
-    if (HALO) halo_wait(P);
+    if (HALO && !halo_wait(P)) return;
     constexpr int W = 2 * T - 4, RS = 2 * T;
     const int tid = threadIdx.x;
     const int y0 = blockIdx.x * W;
@@ -725,6 +739,280 @@ __global__ void __launch_bounds__(T, 4) k_step2x(const __grid_constant__ StepPar
             a0p = sa[0];
             b0p = sb[0];
         }
+    }
+    if (HALO) halo_signal(P);
+}
+
+// -------------------------------------------------------------------------------------------------------
+// D time steps per pass (D = 2, 3, 4): the temporal blocking of k_step2x carried further, so that a cell update
+// moves 144 / D bytes (+ overlap) through DRAM. Same geometry — a block of T threads marches along x over a
+// segment of rows, every thread owns an aligned pair of columns of every intermediate state — but D - 1 rings:
+//   iteration j, phase A : level 1 = row j of S_{t+1} from global S_t (loads issued one row ahead) -> ring 0
+//                __syncthreads (the only one per row)
+//                phase B : level d = 2..D on row j - (2d-3): pulled from ring d-2, collided, stored to ring d-1
+//                          (d < D) or to global S_{t+D} (d = D). Level 2 reads what phase A of this iteration wrote;
+//                          every deeper level reads rows its ring received in EARLIER iterations, so the D - 1 levels
+//                          of phase B are independent of each other (instruction-level parallelism) and need no
+//                          barrier between them.
+// Ring layout: a population written for intermediate row q is read when the consumer reaches row q+1 (5, 8), q (2, 4)
+// or q-1 (6, 7), so 4 / 3 / 2 slots are enough: 18 slot-populations x 2T doubles = 36 KB per ring at T = 128 (24 in
+// k_step2x), which is what lets three blocks of the three-step kernel share an SM. The populations that do not move
+// along y (0, 1, 3) are handed from level to level in registers.
+// Redundant work: 2(D-1) pairs of columns per strip and D-1 rows per level at each end of a segment.
+// FINAL: the last level stops after the moments and writes reference-layout f_post / rho / u of time t+D — how results
+// are materialised after a call that ended on a multi-step pass (the other buffer still holds S_t).
+// -------------------------------------------------------------------------------------------------------
+#ifndef LBM_MERGE_LEVELS
+#define LBM_MERGE_LEVELS 1   // levels 2..D of an iteration in one basic block (instruction-level parallelism over 2(D-1) cells)
+#endif
+#ifndef LBM_LATE_LOAD
+#define LBM_LATE_LOAD 1
+#endif
+#ifndef LBM_D3_MINB
+#define LBM_D3_MINB 2   // resident blocks per SM the three-step kernel is compiled for (register cap 255)
+#endif
+template <int T, int D>
+struct Deep {
+    static constexpr int W = 2 * T - 4 * (D - 1);   // output columns per block
+    static constexpr int RS = 2 * T;                // doubles per ring row
+    static constexpr int SP = 18;                   // slot-populations per ring
+    static constexpr int MINB = D == 2 ? 3 : (D == 3 ? LBM_D3_MINB : 2);
+    static constexpr int SMEM = (D - 1) * SP * RS * (int)sizeof(double);
+};
+
+template <int T, int D, bool HALO, bool PROBE, bool FINAL>
+__global__ void __launch_bounds__(T, Deep<T, D>::MINB) k_stepNx(const __grid_constant__ StepParams P)
+{
+    extern __shared__ double ring[];   // [D-1 rings][18 slot-populations][2T columns]
+    static_assert(D >= 2 && D <= 4, "depth");
+    if (HALO && !halo_wait(P)) return;
+    constexpr int W = Deep<T, D>::W, RS = Deep<T, D>::RS, SP = Deep<T, D>::SP;
+    constexpr bool MERGE = LBM_MERGE_LEVELS != 0;
+    constexpr bool LATE_LOAD = LBM_LATE_LOAD != 0 && D >= 3;
+    const int tid = threadIdx.x;
+    const int y0 = (blockIdx.x + P.strip0) * W;
+    int x0, x1;
+    {
+        const int rb = blockIdx.y;     // segments of the first row range, then of the second one
+        const int nsa = (P.na + P.seg - 1) / P.seg;
+        if (rb < nsa) {
+            x0 = P.row0a + rb * P.seg;
+            x1 = min(x0 + P.seg, P.row0a + P.na);
+        } else {
+            x0 = P.row0b + (rb - nsa) * P.seg;
+            x1 = min(x0 + P.seg, P.row0b + P.nb);
+        }
+    }
+    const int yo = y0 - 2 * (D - 1) + 2 * tid;     // (unwrapped) even column of this thread's pair, at every level
+    const int ca = yo < 0 ? yo + P.NY : (yo >= P.NY ? yo - P.NY : yo);
+    const int cm = ca == 0 ? P.NY - 1 : ca - 1;                  // left neighbour of the pair
+    const int cq = ca + 2 >= P.NY ? ca + 2 - P.NY : ca + 2;      // right neighbour of the pair
+    const long long pl = P.plane;
+
+    auto wrapx = [&](int r) { return r < 0 ? r + P.NX : (r >= P.NX ? r - P.NX : r); };
+    auto load = [&](int j, double (&ga)[9], double (&gb)[9]) {
+        const double *r0 = P.src + (long long)wrapx(j) * P.pitch, *rm = P.src + (long long)wrapx(j - 1) * P.pitch,
+                     *rp = P.src + (long long)wrapx(j + 1) * P.pitch;
+        const double2 v0 = ld2(r0 + ca), v1 = ld2(rm + pl + ca), v3 = ld2(rp + 3 * pl + ca);
+        ga[0] = v0.x; gb[0] = v0.y;
+        ga[1] = v1.x; gb[1] = v1.y;
+        ga[3] = v3.x; gb[3] = v3.y;
+        ga[2] = ldS(r0 + 2 * pl + cm); gb[2] = ldS(r0 + 2 * pl + ca);
+        ga[5] = ldS(rm + 5 * pl + cm); gb[5] = ldS(rm + 5 * pl + ca);
+        ga[6] = ldS(rp + 6 * pl + cm); gb[6] = ldS(rp + 6 * pl + ca);
+        ga[4] = ldS(r0 + 4 * pl + ca + 1); gb[4] = ldS(r0 + 4 * pl + cq);
+        ga[7] = ldS(rp + 7 * pl + ca + 1); gb[7] = ldS(rp + 7 * pl + cq);
+        ga[8] = ldS(rm + 8 * pl + ca + 1); gb[8] = ldS(rm + 8 * pl + cq);
+    };
+    auto prefetch_row = [&](int jj) {   // the nine source segments of level-1 row jj -> L2 (one thread per block)
+        const int c0 = max(y0 - 2 * D, 0);
+        const unsigned bytes = (unsigned)(min(y0 - 2 * (D - 1) + 2 * T + 2, P.pitch) - c0) * 8u;
+        const double *r0 = P.src + (long long)wrapx(jj) * P.pitch + c0, *rm = P.src + (long long)wrapx(jj - 1) * P.pitch + c0,
+                     *rp = P.src + (long long)wrapx(jj + 1) * P.pitch + c0;
+        constexpr int cx[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1};
+#pragma unroll
+        for (int i = 0; i < 9; i++)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((cx[i] == 1 ? rm : (cx[i] == -1 ? rp : r0)) + i * pl), "r"(bytes)
+                         : "memory");
+    };
+    const long long tc = PROBE ? *P.tc_in : 0;
+    auto probe_put = [&](int lvl, double ux, double uy) {   // sample of time t+lvl (redundant rows / columns of
+        double *slot = P.probe + 2 * ((tc + lvl) % P.probe_cap);   // neighbouring blocks write identical values)
+        slot[0] = ux;
+        slot[1] = uy;
+        if (lvl == D) {          // this thread also wrote the samples of t+1 .. t+D-1 (same pair, same row)
+            *P.tc_out = tc + D;
+            publish_progress(P, tc + D);
+        }
+    };
+    // Ring rows hold the even columns of the block in [0, T) and the odd ones in [T, 2T): the +-1 column shifts of the
+    // pulls are then unit-stride 64-bit accesses (no bank conflicts; pairs stored as one 128-bit word cost every
+    // shifted load two extra wavefronts — 2.5e8 conflicts per launch in the first version, profiles/r02_summary.md).
+    const int tm = tid > 0 ? tid - 1 : 0, tp = tid < T - 1 ? tid + 1 : T - 1;   // (clamped: edge pairs compute garbage nobody reads)
+    auto ring_store = [&](int b, unsigned q, const double (&sa)[9], const double (&sb)[9]) {
+        double *R = ring + (size_t)b * SP * RS + tid;
+        const unsigned q3 = q % 3u, q4 = q & 3u, q2 = q & 1u;
+        R[(0 + q3) * RS] = sa[2];   R[(0 + q3) * RS + T] = sb[2];
+        R[(3 + q3) * RS] = sa[4];   R[(3 + q3) * RS + T] = sb[4];
+        R[(6 + q4) * RS] = sa[5];   R[(6 + q4) * RS + T] = sb[5];
+        R[(10 + q4) * RS] = sa[8];  R[(10 + q4) * RS + T] = sb[8];
+        R[(14 + q2) * RS] = sa[6];  R[(14 + q2) * RS + T] = sb[6];
+        R[(16 + q2) * RS] = sa[7];  R[(16 + q2) * RS + T] = sb[7];
+    };
+    // the six y-moving pulls of the pair on intermediate row q: 5, 8 from row q-1; 2, 4 from row q; 6, 7 from row q+1.
+    // Even cell (column 2t): c_y = +1 pulls the odd column of pair t-1, c_y = -1 the odd column of pair t;
+    // odd cell (column 2t+1): c_y = +1 pulls the even column of pair t, c_y = -1 the even column of pair t+1.
+    auto ring_gather = [&](int b, unsigned q, double (&ha)[9], double (&hb)[9]) {
+        const double *R = ring + (size_t)b * SP * RS;
+        const unsigned m3 = q % 3u, a4 = (q - 1u) & 3u, d2 = (q + 1u) & 1u;
+        ha[2] = R[(0 + m3) * RS + T + tm];   hb[2] = R[(0 + m3) * RS + tid];
+        ha[4] = R[(3 + m3) * RS + T + tid];  hb[4] = R[(3 + m3) * RS + tp];
+        ha[5] = R[(6 + a4) * RS + T + tm];   hb[5] = R[(6 + a4) * RS + tid];
+        ha[8] = R[(10 + a4) * RS + T + tid]; hb[8] = R[(10 + a4) * RS + tp];
+        ha[6] = R[(14 + d2) * RS + T + tm];  hb[6] = R[(14 + d2) * RS + tid];
+        ha[7] = R[(16 + d2) * RS + T + tid]; hb[7] = R[(16 + d2) * RS + tp];
+    };
+
+    // unshifted populations in flight between the levels (a = even column, b = odd column of the pair):
+    //   level 1 -> 2: population 0 of row j-1, population 1 of rows j-1 and j-2 (population 3 of row j is fresh)
+    //   level d -> d+1 (d >= 2), w = the row level d wrote last: 3 of row w; 0 of rows w, w-1; 1 of rows w, w-1, w-2
+    double g0a = 0, g0b = 0, g1a[2] = {0, 0}, g1b[2] = {0, 0};
+    double k3a[D] = {}, k3b[D] = {}, k0a[D][2] = {}, k0b[D][2] = {}, k1a[D][3] = {}, k1b[D][3] = {};
+    const int jbeg = x0 - (D - 1), jend = x1 - 1 + (2 * D - 3), l1end = x1 + (D - 1);
+    double fa[9], fb[9];
+    load(jbeg, fa, fb);
+#pragma unroll 1
+    for (int j = jbeg; j <= jend; j++) {
+        const unsigned q = (unsigned)(j - jbeg) + 16u;   // ring row counter of level-1 row j
+        // ---- phase A: level 1, row j (past the end of the segment: harmless recomputation of the last loaded row)
+        double sa[9], sb[9];
+        {
+            if (tid == 0 && P.pf && j + P.pf < l1end) prefetch_row(j + P.pf);
+            double uax, uay, ubx, uby;
+            bool slow_a = false, slow_b = false;
+            relax_fast(fa, P.omega, sa, uax, uay, slow_a);
+            relax_fast(fb, P.omega, sb, ubx, uby, slow_b);
+            if (slow_a | slow_b) {   // operands outside the fast paths' range: never in a physical run
+                if (slow_a) relax_redo(fa, P.omega, sa, uax, uay);
+                if (slow_b) relax_redo(fb, P.omega, sb, ubx, uby);
+            }
+            if (PROBE && j < l1end && wrapx(j) == P.px) {
+                if (ca == P.py) probe_put(1, uax, uay);
+                if (ca + 1 == P.py) probe_put(1, ubx, uby);
+            }
+            if (!LATE_LOAD && j + 1 < l1end) load(j + 1, fa, fb);
+            ring_store(0, q, sa, sb);
+        }
+        __syncthreads();
+        // ---- phase B: levels 2..D, all from ring rows that are complete; computed unconditionally (pipeline fill and
+        // drain, edge pairs: garbage in, garbage out, nothing stored) so that they form ONE basic block
+        double ta[D + 1][9], tb[D + 1][9], vax[D + 1], vay[D + 1], vbx[D + 1], vby[D + 1];
+        double fin_a[9], fin_b[9];   // FINAL: the last level's pulled populations are the result
+        bool slow = false, sl_a[D + 1] = {}, sl_b[D + 1] = {};
+        auto gather_level = [&](int d, double (&ha)[9], double (&hb)[9]) {
+            ring_gather(d - 2, q - (unsigned)(2 * d - 3), ha, hb);
+            if (d == 2) {
+                ha[0] = g0a;    hb[0] = g0b;
+                ha[1] = g1a[1]; hb[1] = g1b[1];
+                ha[3] = sa[3];  hb[3] = sb[3];
+            } else {
+                ha[0] = k0a[d - 2][1]; hb[0] = k0b[d - 2][1];
+                ha[1] = k1a[d - 2][2]; hb[1] = k1b[d - 2][2];
+                ha[3] = k3a[d - 2];    hb[3] = k3b[d - 2];
+            }
+        };
+        auto redo_level = [&](int d) {   // operands outside the fast paths' range (never in a physical run): pull again, library arithmetic
+            const double om = d < D ? P.omega : P.omega_last;
+            double ha[9], hb[9];
+            gather_level(d, ha, hb);
+            if (sl_a[d]) relax_redo(ha, om, ta[d], vax[d], vay[d]);
+            if (sl_b[d]) relax_redo(hb, om, tb[d], vbx[d], vby[d]);
+        };
+        auto store_level = [&](int d) {
+            const int lag = 2 * d - 3, r = j - lag;
+            const bool act = r >= x0 - (D - d) && r < x1 + (D - d);
+            const bool mine = tid >= d - 1 && tid <= T - d && (d < D || yo < P.NY);
+            if (act && mine) {
+                const int xo = wrapx(r);
+                if (PROBE && (d < D || !FINAL) && xo == P.px) {
+                    if (ca == P.py) probe_put(d, vax[d], vay[d]);
+                    if (ca + 1 == P.py) probe_put(d, vbx[d], vby[d]);
+                }
+                if (d < D) {
+                    ring_store(d - 1, q - (unsigned)lag, ta[d], tb[d]);
+                } else if (!FINAL) {
+                    double *o = P.dst + (long long)xo * P.pitch + yo;
+#pragma unroll
+                    for (int i = 0; i < 9; i++) st2(o + i * pl, ta[d][i], tb[d][i]);
+                    if (HALO) {   // (no ghost snapshot: results of a slab are materialised from its own rows only)
+                        store_halo(P, xo, yo, ta[d]);
+                        store_halo(P, xo, yo + 1, tb[d]);
+                    }
+                } else {
+#pragma unroll
+                    for (int c2 = 0; c2 < 2; c2++) {
+                        const double(&h)[9] = c2 ? fin_b : fin_a;
+                        const int y = yo + c2;
+                        if (y < P.oy0 || y >= P.oy0 + P.ow) continue;
+                        double rho, ux, uy;
+                        moments(h, rho, ux, uy);
+                        const long long o = (long long)(xo - P.ox0) * P.ow + (y - P.oy0);
+                        if (P.o_f) {
+#pragma unroll
+                            for (int i = 0; i < 9; i++) P.o_f[o * 9 + i] = h[i];
+                        }
+                        if (P.o_rho) P.o_rho[o] = rho;
+                        if (P.o_u) {
+                            P.o_u[o * 2] = ux;
+                            P.o_u[o * 2 + 1] = uy;
+                        }
+                    }
+                }
+            }
+            if (d < D) {   // hand the unshifted populations of the row just written to level d+1
+                k1a[d - 1][2] = k1a[d - 1][1]; k1a[d - 1][1] = k1a[d - 1][0]; k1a[d - 1][0] = ta[d][1];
+                k1b[d - 1][2] = k1b[d - 1][1]; k1b[d - 1][1] = k1b[d - 1][0]; k1b[d - 1][0] = tb[d][1];
+                k0a[d - 1][1] = k0a[d - 1][0]; k0a[d - 1][0] = ta[d][0];
+                k0b[d - 1][1] = k0b[d - 1][0]; k0b[d - 1][0] = tb[d][0];
+                k3a[d - 1] = ta[d][3];
+                k3b[d - 1] = tb[d][3];
+            }
+        };
+#pragma unroll
+        for (int d = D; d >= 2; d--) {
+            // the next row's loads fly during the LAST level of this phase only (its source segments are in L2
+            // already): the levels before it compute without 36 registers of loads in flight
+            if (LATE_LOAD && d == 2 && j + 1 < l1end) load(j + 1, fa, fb);
+            double ha[9], hb[9];
+            gather_level(d, ha, hb);
+            sl_a[d] = sl_b[d] = false;
+            if (d < D || !FINAL) {
+                const double om = d < D ? P.omega : P.omega_last;
+                relax_fast(ha, om, ta[d], vax[d], vay[d], sl_a[d]);
+                relax_fast(hb, om, tb[d], vbx[d], vby[d], sl_b[d]);
+                slow |= sl_a[d] | sl_b[d];
+            } else {
+#pragma unroll
+                for (int i = 0; i < 9; i++) {
+                    fin_a[i] = ha[i];
+                    fin_b[i] = hb[i];
+                }
+            }
+            if (!MERGE) {   // one basic block per level
+                if (sl_a[d] | sl_b[d]) redo_level(d);
+                store_level(d);
+            }
+        }
+        if (MERGE) {        // all levels of phase B in one basic block: more instruction-level parallelism, more registers
+            if (slow) {
+#pragma unroll
+                for (int d = D; d >= 2; d--) redo_level(d);
+            }
+#pragma unroll
+            for (int d = D; d >= 2; d--) store_level(d);
+        }
+        g1a[1] = g1a[0]; g1a[0] = sa[1]; g0a = sa[0];
+        g1b[1] = g1b[0]; g1b[0] = sb[1]; g0b = sb[0];
     }
     if (HALO) halo_signal(P);
 }
@@ -952,7 +1240,7 @@ __device__ __forceinline__ double bits(unsigned long long sign, unsigned long lo
     return __longlong_as_double((long long)(((sign & 1) << 63) | ((expo & 0x7ff) << 52) | (mant & 0xfffffffffffffULL)));
 }
 
-__global__ void k_selftest_arith(long long n, unsigned long long seed, unsigned long long *out /* [2 counts][4 operands] */)
+__global__ void k_selftest_arith(long long n, unsigned long long seed, unsigned long long *out /* [2 counts][3 operands][2 fast-path counts] */)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -982,6 +1270,24 @@ __global__ void k_selftest_arith(long long n, unsigned long long seed, unsigned 
         const double mine = sqrt_rn(a), ref = __dsqrt_rn(a);
         const bool same = __double_as_longlong(mine) == __double_as_longlong(ref) || (mine != mine && ref != ref);
         if (!same && atomicAdd(out + 1, 1ULL) == 0) out[4] = (unsigned long long)__double_as_longlong(a);
+    }
+    // the branch-free variants of the multi-step kernels: whatever they do not flag as `slow` must be the IEEE result
+    if (is_pos_normal(b)) {
+        bool slow = false;
+        const double mine = div_fast(a, b, rcp_refined(b), slow), ref = __ddiv_rn(a, b);
+        const bool same = __double_as_longlong(mine) == __double_as_longlong(ref) || (mine != mine && ref != ref);
+        if (!slow && !same && atomicAdd(out + 0, 1ULL) == 0) {
+            out[2] = (unsigned long long)__double_as_longlong(a);
+            out[3] = (unsigned long long)__double_as_longlong(b);
+        }
+        if (!slow) atomicAdd(out + 5, 1ULL);   // how many operand pairs took the fast path
+    }
+    {
+        bool slow = false;
+        const double mine = sqrt_fast(a, slow), ref = __dsqrt_rn(a);
+        const bool same = __double_as_longlong(mine) == __double_as_longlong(ref) || (mine != mine && ref != ref);
+        if (!slow && !same && atomicAdd(out + 1, 1ULL) == 0) out[4] = (unsigned long long)__double_as_longlong(a);
+        if (!slow) atomicAdd(out + 6, 1ULL);
     }
 }
 
@@ -1028,6 +1334,7 @@ struct lbm_ctx {
     int bc_mode = LBM_BC_AUTO;
     bool force_generic = false;   // LBM_GENERIC_KERNEL=1: always use the one-cell-per-thread kernel (A/B measurements)
     unsigned *done_counter = nullptr, *err_flag = nullptr;
+    unsigned *err_host = nullptr;   // cudaHostAlloc (mapped): set by a kernel whose halo wait timed out
     long long timeout_cycles = 30LL * 2000000000LL;   // ~30 s at 2 GHz; LBM_HALO_TIMEOUT_S overrides
     // staging for upload / materialize (reference layout, a chunk of rows)
     double *stage_f = nullptr, *stage_rho = nullptr, *stage_u = nullptr;
@@ -1052,8 +1359,10 @@ struct lbm_ctx {
     bool use_fused = true;        // LBM_NO_FUSED=1: one step per pass only (A/B measurements)
     int l2_prefetch = 2;          // rows ahead whose source segments k_step2x prefetches into L2 (option "l2_prefetch")
     int fused_seg = 0;            // output rows per block of the two-step kernel; 0 = pick_seg (LBM_FUSED_SEG / option "fused_seg")
+    int fused_depth = 3;          // time steps per pass of the multi-step kernel, 2..4 (LBM_FUSED_DEPTH / option "fused_depth")
+    bool deep2 = false;           // depth-2 passes through k_stepNx<2> (18-slot ring) instead of k_step2x (option "deep2")
     bool fused_exact = false;     // tests: an even lbm_step(n) is exactly n/2 two-step passes (no one-step tail)
-    bool prev_is_tm1 = false;     // S[cur^1] holds S_{t-1} (false right after a two-step pass or a load)
+    int last_depth = 0;           // S[cur^1] holds S_{t-last_depth}: depth of the pass that produced S_t (0 right after a load)
     // state
     int cur = 0;              // S[cur] = S_t
     bool loaded = false;
@@ -1071,6 +1380,23 @@ struct lbm_ctx {
 static void drop_graphs(lbm_ctx *c);
 static const int kFusedThreads = 128;   // two-steps-per-pass kernel: threads per block
 static const long long kEdgeThreshold = 1 << 20;   // cells; LBM_BC_AUTO switches to the edge kernel above this
+static const int kMaxDepth = 4;         // deepest multi-step pass (k_stepNx)
+
+typedef void (*deep_fn)(const StepParams);
+template <int D>
+static deep_fn deep_kernel_d(bool halo, bool probe, bool final)
+{
+    constexpr int T = kFusedThreads;
+    if (final) return k_stepNx<T, D, false, false, true>;
+    if (halo) return probe ? k_stepNx<T, D, true, true, false> : k_stepNx<T, D, true, false, false>;
+    return probe ? k_stepNx<T, D, false, true, false> : k_stepNx<T, D, false, false, false>;
+}
+static deep_fn deep_kernel(int depth, bool halo, bool probe, bool final)
+{
+    return depth == 2 ? deep_kernel_d<2>(halo, probe, final) : (depth == 3 ? deep_kernel_d<3>(halo, probe, final) : deep_kernel_d<4>(halo, probe, final));
+}
+static int deep_smem(int depth) { return (depth - 1) * 18 * 2 * kFusedThreads * (int)sizeof(double); }
+static int deep_width(int depth) { return 2 * kFusedThreads - 4 * (depth - 1); }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -1160,16 +1486,16 @@ extern "C" int lbm_streaming(int device, int nx, int ny, const double *f, double
     return LBM_OK;
 }
 
-extern "C" int lbm_selftest_arith(int device, int64_t n, uint64_t seed, uint64_t out[5])
+extern "C" int lbm_selftest_arith(int device, int64_t n, uint64_t seed, uint64_t out[7])
 {
     if (n < 0 || !out) return fail(LBM_ERR_ARG, "lbm_selftest_arith: bad argument");
     if (int rc = set_device(device)) return rc;
     DevBuf d;
-    CK(d.alloc(5 * 8));
-    CK(cudaMemset(d.p, 0, 5 * 8));
+    CK(d.alloc(7 * 8));
+    CK(cudaMemset(d.p, 0, 7 * 8));
     if (n) k_selftest_arith<<<(unsigned)((n + 255) / 256), 256>>>(n, seed, d.as<unsigned long long>());
     CK(cudaGetLastError());
-    CK(cudaMemcpy(out, d.p, 5 * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out, d.p, 7 * 8, cudaMemcpyDeviceToHost));
     return LBM_OK;
 }
 
@@ -1249,6 +1575,50 @@ extern "C" int lbm_pbc_apply(int device, int nx, int ny, double rho_in, double r
     return LBM_OK;
 }
 
+// ---- CUDA-IPC mappings ---------------------------------------------------------------------------------------
+// cudaIpcOpenMemHandle may be called once per process and handle: mappings are shared between the neighbour slots (and
+// contexts) that name the same peer arena, counted, and closed when the last user lets go — a later connect with the
+// same handle bytes (re-attach after release_lattices / eviction) opens a fresh mapping instead of finding a dead one.
+struct IpcMapping {
+    std::string key;
+    void *ptr;
+    int refs;
+};
+static std::mutex g_ipc_mutex;
+static std::vector<IpcMapping> g_ipc;
+
+static int ipc_acquire(const uint8_t *handle_bytes, void **out)
+{
+    std::lock_guard<std::mutex> lock(g_ipc_mutex);
+    const std::string key((const char *)handle_bytes, LBM_IPC_HANDLE_BYTES);
+    for (auto &m : g_ipc)
+        if (m.key == key) {
+            m.refs++;
+            *out = m.ptr;
+            return LBM_OK;
+        }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle_bytes, sizeof h);
+    void *p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    g_ipc.push_back({key, p, 1});
+    *out = p;
+    return LBM_OK;
+}
+
+static void ipc_release(void *ptr)
+{
+    std::lock_guard<std::mutex> lock(g_ipc_mutex);
+    for (size_t i = 0; i < g_ipc.size(); i++)
+        if (g_ipc[i].ptr == ptr) {
+            if (--g_ipc[i].refs == 0) {
+                cudaIpcCloseMemHandle(ptr);
+                g_ipc.erase(g_ipc.begin() + i);
+            }
+            return;
+        }
+}
+
 // ---- context -------------------------------------------------------------------------------------------
 extern "C" int lbm_destroy(lbm_ctx *c)
 {
@@ -1258,11 +1628,7 @@ extern "C" int lbm_destroy(lbm_ctx *c)
     if (c->stream_edge) cudaStreamSynchronize(c->stream_edge);
     drop_graphs(c);
     for (int s = 0; s < 9; s++)
-        if (c->peer[s].mapped) {
-            bool shared = false;   // one mapping may serve several slots
-            for (int q = 0; q < s; q++) shared |= c->peer[q].mapped == c->peer[s].mapped;
-            if (!shared) cudaIpcCloseMemHandle(c->peer[s].mapped);
-        }
+        if (c->peer[s].mapped) ipc_release(c->peer[s].mapped);   // every slot holds its own reference
     for (auto &s : c->strips)
         if (s.buf) cudaFree(s.buf);
     void *bufs[] = {c->arena,  c->kind_map, c->kinds,    c->ktab,   c->ctab,  c->outbuf[0],   c->outbuf[1], c->outbuf[2], c->cells, c->snap_row, c->snap_col,
@@ -1271,6 +1637,7 @@ extern "C" int lbm_destroy(lbm_ctx *c)
         if (b) cudaFree(b);
     if (c->probe) cudaFreeHost(c->probe);
     if (c->progress) cudaFreeHost(c->progress);
+    if (c->err_host) cudaFreeHost(c->err_host);
     if (c->ev_main) cudaEventDestroy(c->ev_main);
     if (c->ev_edge) cudaEventDestroy(c->ev_edge);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -1375,6 +1742,10 @@ static int ctx_build(lbm_ctx *c, const lbm_bc_desc *bc)
         CK(cudaFuncSetAttribute(k_step2x<kFusedThreads, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         CK(cudaFuncSetAttribute(k_step2x<kFusedThreads, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         CK(cudaFuncSetAttribute(k_step2x<kFusedThreads, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        for (int d = 2; d <= kMaxDepth; d++)
+            for (int v = 0; v < 5; v++)
+                CK(cudaFuncSetAttribute((const void *)deep_kernel(d, v & 1, (v >> 1) & 1, v == 4), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        deep_smem(d)));
     }
 
     const size_t sbytes = (size_t)9 * c->plane * 8;
@@ -1403,6 +1774,8 @@ static int ctx_build(lbm_ctx *c, const lbm_bc_desc *bc)
     CK(cudaMemsetAsync(c->tcount, 0, 24, c->stream));
     CK(cudaHostAlloc((void **)&c->progress, 64, cudaHostAllocMapped));
     *c->progress = 0;
+    CK(cudaHostAlloc((void **)&c->err_host, 64, cudaHostAllocMapped));
+    *c->err_host = 0;
     for (int b = 0; b < 3; b++) {
         CK(cudaMalloc(&c->outbuf[b], (size_t)3 * c->pitch * 8));
         CK(cudaMemsetAsync(c->outbuf[b], 0, (size_t)3 * c->pitch * 8, c->stream));
@@ -1477,9 +1850,9 @@ extern "C" int lbm_create(int device, int nx, int ny, int ghost_x, int ghost_y, 
     if (!out) return fail(LBM_ERR_ARG, "lbm_create: out is null");
     *out = nullptr;
     if (nx < 1 || ny < 1) return fail(LBM_ERR_ARG, "lbm_create: lattice must be at least 1x1 (got %dx%d)", nx, ny);
-    if (ghost_x < 0 || ghost_x > 2 || (ghost_y & ~1)) return fail(LBM_ERR_ARG, "lbm_create: ghost_x must be 0, 1 or 2 and ghost_y 0 or 1");
-    if (ghost_x == 2 && (ghost_y || (bc && bc->kind_map)))
-        return fail(LBM_ERR_ARG, "lbm_create: two ghost rows (two-steps-per-pass slabs) exist for fluid lattices without y ghosts only");
+    if (ghost_x < 0 || ghost_x > kMaxDepth || (ghost_y & ~1)) return fail(LBM_ERR_ARG, "lbm_create: ghost_x must be 0..%d and ghost_y 0 or 1", kMaxDepth);
+    if (ghost_x >= 2 && (ghost_y || (bc && bc->kind_map)))
+        return fail(LBM_ERR_ARG, "lbm_create: %d ghost rows (slabs of the multi-step kernel) exist for fluid lattices without y ghosts only", ghost_x);
     if ((ghost_x && nx < 4 * ghost_x) || (ghost_y && ny < 3)) return fail(LBM_ERR_ARG, "lbm_create: too few interior cells for the ghost ring");
     lbm_ctx *c = new lbm_ctx;
     c->device = device;
@@ -1493,6 +1866,8 @@ extern "C" int lbm_create(int device, int nx, int ny, int ghost_x, int ghost_y, 
     if (const char *g = getenv("LBM_NO_GRAPHS")) c->use_graphs = atoi(g) == 0;
     if (const char *g = getenv("LBM_NO_FUSED")) c->use_fused = atoi(g) == 0;
     if (const char *g = getenv("LBM_FUSED_SEG")) c->fused_seg = atoi(g) >= 2 ? atoi(g) : 0;
+    if (const char *g = getenv("LBM_FUSED_DEPTH")) c->fused_depth = std::min(kMaxDepth, std::max(2, atoi(g)));
+    if (const char *g = getenv("LBM_DEEP2")) c->deep2 = atoi(g) != 0;
     if (const char *t = getenv("LBM_HALO_TIMEOUT_S")) c->timeout_cycles = (long long)(atof(t) * 2e9);
     if (int rc = ctx_build(c, bc)) {
         std::string keep = g_err;
@@ -1530,11 +1905,16 @@ extern "C" int lbm_set_option(lbm_ctx *c, const char *name, int value)
     else if (n == "l2_prefetch") {
         if (value < 0 || value > 8) return fail(LBM_ERR_ARG, "lbm_set_option: l2_prefetch must be 0..8 rows");
         c->l2_prefetch = value;
+    } else if (n == "fused_depth") {
+        if (value < 2 || value > kMaxDepth) return fail(LBM_ERR_ARG, "lbm_set_option: fused_depth must be 2..%d", kMaxDepth);
+        c->fused_depth = value;
+    } else if (n == "deep2") {
+        c->deep2 = value != 0;
     } else if (n == "fused_seg") {
         if (value < 2 && value != 0) return fail(LBM_ERR_ARG, "lbm_set_option: fused_seg must be >= 2, or 0 for the default");
         c->fused_seg = value;
     } else
-        return fail(LBM_ERR_ARG, "lbm_set_option: unknown option '%s' (fused, graphs, pdl, generic_kernel, fused_exact, fused_seg, l2_prefetch)", name);
+        return fail(LBM_ERR_ARG, "lbm_set_option: unknown option '%s' (fused, graphs, pdl, generic_kernel, fused_exact, fused_seg, fused_depth, deep2, l2_prefetch)", name);
     return LBM_OK;
 }
 
@@ -1564,6 +1944,7 @@ static void fill_common(const lbm_ctx *c, StepParams &P, int src_buf, int dst_bu
     P.gx = c->gx;
     P.gy = c->gy;
     P.omega = omega;
+    P.omega_last = omega;
     P.kind_map = c->has_bc ? c->kind_map : nullptr;
     P.kinds = c->kinds;
     P.ktab = c->ktab;
@@ -1582,6 +1963,7 @@ static void fill_common(const lbm_ctx *c, StepParams &P, int src_buf, int dst_bu
     P.done_counter = c->done_counter;
     P.timeout_cycles = c->timeout_cycles;
     P.err_flag = c->err_flag;
+    P.err_host = c->err_host;
     P.flag_in = c->flags_in;
 }
 
@@ -1755,6 +2137,19 @@ static bool fused_ok(const lbm_ctx *c)
            (c->NX - 2 * c->gx) >= 8 && (long long)c->NX * c->NY >= kEdgeThreshold && (!c->gx || c->halo_ready);
 }
 
+// May a call END on a multi-step pass? Yes where results of time t can be rebuilt from S_{t-d} by re-running the pass
+// with its last level in FINAL mode: fluid lattices (slabs expose their own rows only). Lattices with boundary cells
+// (strip windows) end every call with a one-step launch instead, unless option fused_exact says otherwise.
+static bool tail_free(const lbm_ctx *c) { return !c->has_bc; }
+
+// Deepest pass this lattice can take: lattices with boundary cells stay on two steps (strip windows), slabs cannot look
+// further than their ghost rows.
+static int max_depth(const lbm_ctx *c)
+{
+    if (c->has_bc) return 2;
+    return c->gx ? std::min(c->gx, c->fused_depth) : c->fused_depth;
+}
+
 // Output rows per thread block of the two-step kernel. Every block recomputes one intermediate row at each end of
 // its segment (2 / seg redundant work), but a lattice of a few million cells needs short segments to fill the
 // 148 SMs x 4 resident blocks several times over. Measured (tools/fused_sweep.py, profiles/r01c_fused_sweep.txt):
@@ -1764,16 +2159,32 @@ static int pick_seg(const lbm_ctx *c, int rows)
 {
     if (c->fused_seg) return c->fused_seg;
     const long long strips = (c->NY + 2 * kFusedThreads - 5) / (2 * kFusedThreads - 4);
-    int seg = 64;
+    int seg = 256;
     while (seg > 8 && strips * ((rows + seg - 1) / seg) < 2000) seg /= 2;
     return seg;
 }
 
 template <bool HALO>
-static int fused_launch(lbm_ctx *c, StepParams P, int row0a, int na, int row0b, int nb, int seg, cudaStream_t st)
+static int fused_launch(lbm_ctx *c, StepParams P, int row0a, int na, int row0b, int nb, int seg, cudaStream_t st, int depth = 2)
 {
     if (na + nb <= 0) return LBM_OK;
     constexpr int T = kFusedThreads;
+    if (depth > 2 || c->deep2) {   // k_stepNx
+        P.row0a = row0a;
+        P.na = na;
+        P.row0b = row0b;
+        P.nb = nb;
+        P.seg = seg;
+        P.pf = c->l2_prefetch;
+        const int W = deep_width(depth);
+        dim3 grid((c->NY + W - 1) / W, (na + seg - 1) / seg + (nb + seg - 1) / seg);
+        P.n_blocks = (int)(grid.x * grid.y);
+        deep_kernel(depth, HALO, P.probe != nullptr, false)<<<grid, T, deep_smem(depth), st>>>(P);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "%d-step kernel launch failed: %s", depth, cudaGetErrorString(e));
+        c->launches++;
+        return LBM_OK;
+    }
     const size_t smem = (size_t)4 * 6 * 2 * T * sizeof(double);
     // (the opt-in to > 48 KB of dynamic shared memory is done once per device in ctx_build: cudaFuncSetAttribute
     //  may wait for the device, and a neighbour's kernel may be spinning on a flag this rank has yet to publish)
@@ -1835,15 +2246,16 @@ static int two_steps_bc(lbm_ctx *c, const StepParams &P0, int src, int dst)
     return LBM_OK;
 }
 
-static int two_steps(lbm_ctx *c, int src, double omega)
+static int two_steps(lbm_ctx *c, int src, double omega, int depth = 2, double omega_last = 0.0)
 {
     const int dst = src ^ 1;
     StepParams P;
     fill_common(c, P, src, dst, omega);
+    if (omega_last != 0.0) P.omega_last = omega_last;   // redo of a pass whose last collision must use the caller's new omega
     if (c->has_bc) return two_steps_bc(c, P, src, dst);
     set_probe(c, P, src, dst);
     const int g = c->gx, xlo = g, xhi = c->NX - g;
-    if (!g) return fused_launch<false>(c, P, xlo, xhi - xlo, 0, 0, pick_seg(c, xhi - xlo), c->stream);
+    if (!g) return fused_launch<false>(c, P, xlo, xhi - xlo, 0, 0, pick_seg(c, xhi - xlo), c->stream, depth);
     // two-row slabs: the 2 + 2 edge rows (readers of the ghost rows, writers of the neighbours') first on the
     // high-priority stream with the flag handshake, the interior overlaps with their NVLink stores
     const bool remote = c->any_remote;
@@ -1856,11 +2268,11 @@ static int two_steps(lbm_ctx *c, int src, double omega)
         Pe.wait_value = E;
         Pe.signal_value = E + 1;
     }
-    if (int rc = fused_launch<true>(c, Pe, xlo, g, xhi - g, g, g, c->stream_edge)) return rc;
+    if (int rc = fused_launch<true>(c, Pe, xlo, g, xhi - g, g, g, c->stream_edge, depth)) return rc;
     CK(cudaEventRecord(c->ev_edge, c->stream_edge));
     StepParams Pi = P;
     for (int s = 0; s < 9; s++) Pi.halo[s].base = nullptr;
-    if (int rc = fused_launch<false>(c, Pi, xlo + g, xhi - xlo - 2 * g, 0, 0, pick_seg(c, xhi - xlo - 2 * g), c->stream)) return rc;
+    if (int rc = fused_launch<false>(c, Pi, xlo + g, xhi - xlo - 2 * g, 0, 0, pick_seg(c, xhi - xlo - 2 * g), c->stream, depth)) return rc;
     CK(cudaStreamWaitEvent(c->stream, c->ev_edge, 0));
     if (remote) c->halo_epoch++;
     return LBM_OK;
@@ -1890,6 +2302,9 @@ static int begin_load(lbm_ctx *c, double omega, InitParams &Q)
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaStreamSynchronize(c->stream_edge));
+    CK(cudaMemsetAsync(c->err_flag, 0, 4, c->stream));
+    CK(cudaMemsetAsync(c->done_counter, 0, 8, c->stream));
+    *c->err_host = 0;
     memset(&Q, 0, sizeof Q);
     c->cur = 0;
     fill_common(c, Q.S, 1, 0, omega);   // "dst" = S[0]; outlet buffer written = outbuf[0], read by the first step
@@ -1904,7 +2319,7 @@ static int end_load(lbm_ctx *c, double omega)
     *c->progress = 0;
     c->loaded = true;
     c->t = 0;
-    c->prev_is_tm1 = false;
+    c->last_depth = 0;
     c->omega = omega;
     // Ghost stores of the first collision are ordered against the first step by a host-side barrier the caller
     // performs (python: process-group barrier after upload); flags restart from a common epoch.
@@ -2001,6 +2416,18 @@ static int graph_for(lbm_ctx *c, double omega, lbm_ctx::GraphEntry **out)
     return LBM_OK;
 }
 
+// A halo wait that timed out is reported by every later call that looks at the lattice (sticky until the next load):
+// the kernels after the failed wait have not computed anything (halo_wait), so the state is unusable.
+static int async_error(lbm_ctx *c, const char *who)
+{
+    const unsigned err = c->err_host ? *(volatile unsigned *)c->err_host : 0u;
+    if (!err) return LBM_OK;
+    return fail(LBM_ERR_TIMEOUT,
+                "%s: halo flag wait timed out — a neighbouring rank did not take the same step (waited for step %u of neighbour "
+                "slot %u; my step count %u). The lattice state is invalid: load it again on every rank.",
+                who, (err >> 8) & 0x7fffff, err & 0xff, c->halo_epoch);
+}
+
 extern "C" int lbm_step(lbm_ctx *c, double omega, int n_steps)
 {
     if (!c) return fail(LBM_ERR_ARG, "lbm_step: null context");
@@ -2008,12 +2435,19 @@ extern "C" int lbm_step(lbm_ctx *c, double omega, int n_steps)
     if (n_steps < 0) return fail(LBM_ERR_ARG, "lbm_step: n_steps < 0");
     if (!c->loaded) return fail(LBM_ERR_STATE, "lbm_step before lbm_upload / lbm_init_equilibrium");
     if (n_steps == 0) return LBM_OK;
+    if (int rc = async_error(c, "lbm_step")) return rc;
     CK(cudaSetDevice(c->device));
     if (omega != c->omega) {
-        // S[cur] was collided with the previous call's omega. Redo that collision from the retained S_{t-1}.
-        if (c->t == 0 || !c->prev_is_tm1) return fail(LBM_ERR_STATE, "omega differs from the one the resident state was collided with and the previous state is not retained: upload again");
+        // S[cur] was collided with the previous call's omega. Redo that collision from the retained S_{t-d}: the last
+        // launch again (a one-step launch, or a multi-step pass whose LAST level collides with the new omega).
+        if (c->t == 0 || c->last_depth < 1 || (c->last_depth > 1 && c->has_bc))
+            return fail(LBM_ERR_STATE, "omega differs from the one the resident state was collided with and the previous state is not retained: upload again");
         if (c->any_remote) return fail(LBM_ERR_STATE, "changing omega between steps is not supported with remote halo neighbours: upload again");
-        if (int rc = one_step(c, c->cur ^ 1, omega, c->t)) return rc;
+        if (c->last_depth == 1) {
+            if (int rc = one_step(c, c->cur ^ 1, omega, c->t)) return rc;
+        } else {
+            if (int rc = two_steps(c, c->cur ^ 1, c->omega, c->last_depth, omega)) return rc;
+        }
         c->omega = omega;
     }
     int left = n_steps;
@@ -2025,25 +2459,32 @@ extern "C" int lbm_step(lbm_ctx *c, double omega, int n_steps)
             c->launches += g->launches;
             c->t += kGraphSteps;
             left -= kGraphSteps;
-            c->prev_is_tm1 = true;
+            c->last_depth = 1;
         }
     }
     // Bandwidth-bound fluid lattices advance two steps per pass; the call always ENDS with a one-step launch so that
     // the other buffer holds S_{t-1}, from which results are materialised and a changed omega is redone.
-    if (fused_ok(c) && (left >= 3 || (c->fused_exact && left >= 2))) {
-        for (int pairs = c->fused_exact && left % 2 == 0 ? left / 2 : (left - 1) / 2; pairs > 0; pairs--) {
-            if (int rc = two_steps(c, c->cur, omega)) return rc;
+    // Bandwidth-bound lattices advance D steps per pass. Fluid lattices may end a call on a pass (results are then
+    // materialised by re-running it in FINAL mode, a changed omega redoes its last level); lattices with boundary
+    // cells end every call with a one-step launch so that the other buffer holds S_{t-1}.
+    if (fused_ok(c)) {
+        const int D = max_depth(c);
+        const bool no_tail = tail_free(c) || c->fused_exact;
+        while (true) {
+            const int d = std::min(D, no_tail ? left : left - 1);
+            if (d < 2) break;
+            if (int rc = two_steps(c, c->cur, omega, d)) return rc;
             c->cur ^= 1;
-            c->t += 2;
-            left -= 2;
-            c->prev_is_tm1 = false;
+            c->t += d;
+            left -= d;
+            c->last_depth = d;
         }
     }
     for (int i = 0; i < left; i++) {
         if (int rc = one_step(c, c->cur, omega, c->t + 1)) return rc;
         c->cur ^= 1;
         c->t++;
-        c->prev_is_tm1 = true;
+        c->last_depth = 1;
     }
     return LBM_OK;
 }
@@ -2054,19 +2495,7 @@ extern "C" int lbm_sync(lbm_ctx *c)
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream_edge));
     CK(cudaStreamSynchronize(c->stream));
-    unsigned err = 0;
-    CK(cudaMemcpy(&err, c->err_flag, 4, cudaMemcpyDeviceToHost));
-    if (err) {
-        unsigned fl[9] = {0};
-        cudaMemcpy(fl, c->flags_in, sizeof fl, cudaMemcpyDeviceToHost);
-        cudaMemsetAsync(c->err_flag, 0, 4, c->stream);
-        cudaStreamSynchronize(c->stream);
-        return fail(LBM_ERR_TIMEOUT,
-                    "halo flag wait timed out: a neighbouring rank did not take the same step (waited for step %u of "
-                    "neighbour slot %u; flags now %u %u %u %u . %u %u %u %u; my step count %u)",
-                    (err >> 8) & 0x7fffff, err & 0xff, fl[0], fl[1], fl[2], fl[3], fl[5], fl[6], fl[7], fl[8], c->halo_epoch);
-    }
-    return LBM_OK;
+    return async_error(c, "lbm_sync");
 }
 
 // f_post / rho / u of time t are stream+BC+moments of S_{t-1}, which the A/B scheme still holds in S[cur^1].
@@ -2092,7 +2521,22 @@ static int materialize_rows(lbm_ctx *c, int x0, int x1, int y0, int y1, double *
         P.o_rho = rho || !to_host ? c->stage_rho : nullptr;
         P.o_u = u || !to_host ? c->stage_u : nullptr;
         const int blocks = nr * P.bpr;
-        cudaError_t e = c->has_bc ? launch<true, false, true, false>(P, blocks, bs, c->stream) : launch<false, false, true, false>(P, blocks, bs, c->stream);
+        cudaError_t e;
+        if (c->last_depth > 1) {
+            // the call ended on a multi-step pass: S[cur^1] is S_{t-d}. Re-run the pass over these rows with its last level
+            // in FINAL mode (f_post / rho / u of time t instead of the collision), column strips that meet [y0, y1) only
+            const int d = c->last_depth, W = deep_width(d);
+            P.use_snap = 0;
+            P.row0b = 0;
+            P.nb = 0;
+            P.seg = std::min(nr, 64);
+            P.pf = 0;
+            P.strip0 = y0 / W;
+            dim3 grid((y1 + W - 1) / W - P.strip0, (nr + P.seg - 1) / P.seg);
+            deep_kernel(d, false, false, true)<<<grid, kFusedThreads, deep_smem(d), c->stream>>>(P);
+            e = cudaGetLastError();
+        } else
+            e = c->has_bc ? launch<true, false, true, false>(P, blocks, bs, c->stream) : launch<false, false, true, false>(P, blocks, bs, c->stream);
         if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "materialize kernel launch failed: %s", cudaGetErrorString(e));
         c->launches++;
         const size_t n = (size_t)nr * w, o = (size_t)(xa - x0) * w;
@@ -2109,16 +2553,16 @@ static int materialize_rows(lbm_ctx *c, int x0, int x1, int y0, int y1, double *
             CK(cudaStreamSynchronize(c->stream));
         }
     }
-    return LBM_OK;
+    return async_error(c, "lbm_materialize");
 }
 
 static int check_region(lbm_ctx *c, int x0, int x1, int y0, int y1, const char *who)
 {
     if (!c) return fail(LBM_ERR_ARG, "%s: null context", who);
     if (!c->loaded || c->t == 0) return fail(LBM_ERR_STATE, "%s: no step taken since the state was loaded — the caller still holds it", who);
-    if (!c->prev_is_tm1) return fail(LBM_ERR_STATE, "%s: the last launch was a two-step pass (fused_exact): take one more step first", who);
+    if (c->last_depth > 1 && c->has_bc) return fail(LBM_ERR_STATE, "%s: the last launch was a multi-step pass on a lattice with boundary cells (fused_exact): take one more step first", who);
     if (x0 < 0 || y0 < 0 || x1 > c->NX || y1 > c->NY || x0 >= x1 || y0 >= y1) return fail(LBM_ERR_ARG, "%s: empty or out-of-range region", who);
-    if (c->gx == 2 && (x0 < 2 || x1 > c->NX - 2)) return fail(LBM_ERR_ARG, "%s: two-row slabs expose their interior rows [2, nx-2) only", who);
+    if (c->gx >= 2 && (x0 < c->gx || x1 > c->NX - c->gx)) return fail(LBM_ERR_ARG, "%s: slabs with %d ghost rows expose their interior rows [%d, nx-%d) only", who, c->gx, c->gx, c->gx);
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream_edge));
     return LBM_OK;
@@ -2165,7 +2609,9 @@ extern "C" int lbm_probe_config(lbm_ctx *c, int x, int y, int capacity)
     c->px = x;
     c->py = y;
     c->probe_cap = capacity;
-    const long long tt[3] = {c->t, c->t, c->t};
+    // S[cur] holds time t, S[cur^1] time t-1 (the launch an omega change redoes reads it and must land on t again)
+    long long tt[3] = {c->t, c->t, c->t};
+    tt[c->cur ^ 1] = c->t - 1;
     CK(cudaMemcpyAsync(c->tcount, tt, 24, cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     drop_graphs(c);
@@ -2184,13 +2630,14 @@ extern "C" int lbm_probe_read(lbm_ctx *c, int64_t t0, int n, double *uxuy)
     // streams have drained, everything that was ever going to be recorded is in the ring.)
     const long long target = t0 + n - 1;
     volatile long long *progress = c->progress;
-    while (*progress < target) {
+    while (*progress < target && !*(volatile unsigned *)c->err_host) {
         const cudaError_t a = cudaStreamQuery(c->stream_edge), b = cudaStreamQuery(c->stream);
         if (a != cudaSuccess && a != cudaErrorNotReady) CK(a);
         if (b != cudaSuccess && b != cudaErrorNotReady) CK(b);
         if (a == cudaSuccess && b == cudaSuccess) break;
     }
     __sync_synchronize();
+    if (int rc = async_error(c, "lbm_probe_read")) return rc;
     for (int i = 0; i < n;) {
         const int slot = (int)((t0 + i) % c->probe_cap);
         const int run = std::min(n - i, c->probe_cap - slot);
@@ -2249,17 +2696,10 @@ extern "C" int lbm_halo_connect(lbm_ctx *c, int slot, const lbm_halo_export *pee
         }
     } else {
         // reuse a mapping of the same peer opened for another slot (cudaIpcOpenMemHandle is once per process)
+        if (pr.mapped) ipc_release(pr.mapped);   // slot re-connected
+        pr.mapped = nullptr;
         void *m = nullptr;
-        static thread_local std::vector<std::pair<std::string, void *>> opened;
-        const std::string key((const char *)peer->mem_handle, LBM_IPC_HANDLE_BYTES);
-        for (auto &kv : opened)
-            if (kv.first == key) m = kv.second;
-        if (!m) {
-            cudaIpcMemHandle_t h;
-            memcpy(&h, peer->mem_handle, sizeof h);
-            CK(cudaIpcOpenMemHandle(&m, h, cudaIpcMemLazyEnablePeerAccess));
-            opened.emplace_back(key, m);
-        }
+        if (int rc = ipc_acquire(peer->mem_handle, &m)) return rc;
         pr.mapped = m;
         pr.arena = (char *)m;
         pr.remote = true;

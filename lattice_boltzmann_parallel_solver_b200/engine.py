@@ -287,9 +287,12 @@ _SHAPES = {'f': lambda nx, ny: (nx, ny, 9), 'rho': lambda nx, ny: (nx, ny), 'u':
 
 
 class LatticeArray(np.lib.mixins.NDArrayOperatorsMixin):
-    """ndarray-like view of one field of a `Lattice` at one time. Read-only until materialised; any numpy
-    operation materialises it (one device->host copy, cached) — except scalar cell reads and whole-field
-    np.amin / np.amax, which are answered from the device."""
+    """ndarray-like view of one field of a `Lattice` at one time. Any numpy operation materialises it (one
+    device->host copy, cached) — except scalar cell reads and whole-field np.amin / np.amax, which are answered from
+    the device. `np.asarray(handle)` is the cached, READ-ONLY host copy (take `.copy()` to edit it); in-place edits
+    through the handle itself (`h[i] = v`, `h += x`, `np.add(h, x, out=h)`) work as on the reference's arrays: the
+    handle switches to a private writable copy and stops counting as the device's current state, so feeding it back
+    into `lattice_boltzmann_step` uploads it."""
 
     __array_priority__ = 100
 
@@ -329,11 +332,27 @@ class LatticeArray(np.lib.mixins.NDArrayOperatorsMixin):
             return a.astype(dtype)
         return a.copy() if copy else a
 
+    def _writable(self):
+        """The host copy, made writable and marked as diverged from the device (in-place edits: f += x, out=f)."""
+        a = self.materialize()
+        if not a.flags.writeable:
+            a = self._value = a.copy()
+        self._dirty = True
+        return a
+
     def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
         inputs = tuple(x.materialize() if isinstance(x, LatticeArray) else x for x in inputs)
-        if 'out' in kwargs:
-            kwargs['out'] = tuple(x.materialize() if isinstance(x, LatticeArray) else x for x in kwargs['out'])
-        return getattr(ufunc, method)(*inputs, **kwargs)
+        outs = kwargs.get('out')
+        if outs is not None:
+            # the reference's results are ordinary writable ndarrays: `f += x` / np.add(f, x, out=f) must work on a
+            # handle too. The handle then owns a private host copy and no longer counts as the device's current state.
+            kwargs['out'] = tuple(x._writable() if isinstance(x, LatticeArray) else x for x in outs)
+        res = getattr(ufunc, method)(*inputs, **kwargs)
+        if outs is not None and any(isinstance(x, LatticeArray) for x in outs):
+            if isinstance(res, tuple):
+                return tuple(o if isinstance(o, LatticeArray) else r for o, r in zip(outs, res))
+            return outs[0] if isinstance(outs[0], LatticeArray) else res
+        return res
 
     def __array_function__(self, func, types, args, kwargs):
         if func in (np.amin, np.amax, np.min, np.max) and len(args) == 1 and not kwargs and args[0] is self \
@@ -382,11 +401,7 @@ class LatticeArray(np.lib.mixins.NDArrayOperatorsMixin):
         return self.materialize()[index]
 
     def __setitem__(self, index, value):
-        a = self.materialize()
-        if not a.flags.writeable:
-            a = self._value = a.copy()
-        self._dirty = True
-        a[index] = value
+        self._writable()[index] = value
 
     def __len__(self):
         return self.shape[0]

@@ -69,12 +69,14 @@ def test_hand_expanded_division_and_sqrt_equal_ieee(P):
     import struct
     from lattice_boltzmann_parallel_solver_b200 import _native as N
     lib = N.load()
-    out = (C.c_uint64 * 5)()
+    out = (C.c_uint64 * 7)()
     for seed in (1, 20261017, 0xdeadbeefcafe):
         N.check(lib.lbm_selftest_arith(N.device(), 1 << 27, seed, out))
         as_f = [struct.unpack('<d', struct.pack('<Q', v))[0] for v in out[2:5]]
         assert out[0] == 0, f'{out[0]} quotients differ from __ddiv_rn, first: {as_f[0]!r} / {as_f[1]!r} ({out[2]:#x}, {out[3]:#x})'
         assert out[1] == 0, f'{out[1]} roots differ from __dsqrt_rn, first: sqrt({as_f[2]!r}) ({out[4]:#x})'
+        # the branch-free variants must answer the bulk themselves (physical range, exact quotients, zeros, ...)
+        assert out[5] > (1 << 27) // 3 and out[6] > (1 << 27) // 4, (out[5], out[6])
 
 
 def test_equilibrium_1d_inputs(P, oracle):
@@ -532,6 +534,7 @@ def test_two_steps_per_pass_equals_single_steps(P, oracle, shape):
     f, rho, u = random_state(oracle, shape, 21)
     from lattice_boltzmann_parallel_solver_b200.engine import Lattice
     fused = Lattice(*shape)
+    fused.set_option('fused_depth', 2)
     plain = _lattice_with_env(shape, {'LBM_NO_FUSED': '1'}) if shape[0] == 1024 else Lattice(*shape)
     plain.set_option('fused', 0)
     px, py = shape[0] // 3, shape[1] - 2
@@ -539,10 +542,10 @@ def test_two_steps_per_pass_equals_single_steps(P, oracle, shape):
         lat.probe(px, py, capacity=64)
         lat.load(f, rho, u, 1.37)
     l0 = fused.launches
-    for n in (7, 1, 8, 2):            # odd and even counts: 3 pairs + 1, a lone step, 3 pairs + 2, two single steps
-        fused.run(n)
+    for n in (7, 1, 8, 2):            # odd and even counts: 3 pairs + 1, a lone step, 4 pairs, 1 pair (a fluid lattice
+        fused.run(n)                  # may end a call on a pass: results are then rebuilt by re-running it in FINAL mode)
         plain.run(n)
-    assert fused.launches - l0 == (3 + 1) + 1 + (3 + 2) + 2, 'the two-step kernel was not used'
+    assert fused.launches - l0 == (3 + 1) + 1 + 4 + 1, 'the two-step kernel was not used'
     for a, b, nm in zip(fused.fields(), plain.fields(), 'f rho u'.split()):
         assert_parity(a, b, f'{shape} {nm}')
     assert_parity(fused.probe_read(1, 18), plain.probe_read(1, 18), 'probe ring')
@@ -552,6 +555,84 @@ def test_two_steps_per_pass_equals_single_steps(P, oracle, shape):
             assert_parity(a, b, f'vs oracle {nm}')
     fused.close()
     plain.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# D steps per pass (k_stepNx, D = 2, 3, 4) == D one-step passes == the C oracle, on random (x- and y-varying) fields
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('depth', [2, 3, 4])
+@pytest.mark.parametrize('shape', [(1024, 1024), (4100, 258), (513, 2050)])
+def test_deep_passes_equal_single_steps(P, oracle, shape, depth):
+    f, rho, u = random_state(oracle, shape, 31 + depth)
+    from lattice_boltzmann_parallel_solver_b200.engine import Lattice
+    fused, plain = Lattice(*shape), Lattice(*shape)
+    fused.set_option('fused_depth', depth)
+    fused.set_option('deep2', 1)
+    plain.set_option('fused', 0)
+    px, py = shape[0] // 3, shape[1] - 2
+    for lat in (fused, plain):
+        lat.probe(px, py, capacity=64)
+        lat.load(f, rho, u, 1.37)
+    total = 0
+    for n in (2 * depth + 1, 1, 3 * depth, 2, depth + 2):
+        fused.run(n)
+        plain.run(n)
+        total += n
+    assert fused.launches < plain.launches, 'the multi-step kernel was not used'
+    for a, b, nm in zip(fused.fields(), plain.fields(), 'f rho u'.split()):
+        assert_parity(a, b, f'{shape} depth {depth} {nm}')
+    assert_parity(fused.probe_read(1, total), plain.probe_read(1, total), 'probe ring')
+    if shape == (1024, 1024):
+        ref = oracle.c.run(f, rho, u, 1.37, oracle.c.periodic(), total)
+        for a, b, nm in zip(fused.fields(), ref, 'f rho u'.split()):
+            assert_parity(a, b, f'vs oracle {nm}')
+    fused.close()
+    plain.close()
+
+
+@pytest.mark.parametrize('depth,seg,tail', [(2, 16, 1), (2, 64, 0), (3, 16, 0), (3, 32, 1), (3, 64, 1), (3, 128, 0), (3, 256, 1),
+                                            (4, 64, 0)])
+def test_deep_passes_segment_lengths(P, oracle, depth, seg, tail):
+    """The launch geometry of the headline (long segments, which pick_seg only chooses from 8192^2 up) on a random
+    field at 4096 x 512, against the C oracle: a row mix-up inside a segment cannot hide here."""
+    from lattice_boltzmann_parallel_solver_b200.engine import Lattice
+    shape = (4096, 512)
+    f, rho, u = random_state(oracle, shape, 77)
+    lat = Lattice(*shape)
+    lat.set_option('fused_depth', depth)
+    lat.set_option('deep2', 1)
+    lat.set_option('fused_seg', seg)
+    lat.load(f, rho, u, 0.9)
+    steps = 2 * depth + tail          # tail = 0: the call ENDS on a pass and fields() re-runs it in FINAL mode
+    l0 = lat.launches
+    lat.run(steps)
+    assert lat.launches - l0 == 2 + tail, 'two multi-step passes (and one single step) expected'
+    ref = oracle.c.run(f, rho, u, 0.9, oracle.c.periodic(), steps)
+    for a, b, nm in zip(lat.fields(), ref, 'f rho u'.split()):
+        assert_parity(a, b, f'depth {depth} seg {seg} {nm}')
+    got = lat.fields(region=(1000, 1003, 250, 259))          # a sub-rectangle that straddles two column strips
+    for a, b, nm in zip(got, ref, 'f rho u'.split()):
+        assert_parity(a, b[1000:1003, 250:259], f'region {nm}')
+    mn_r, mx_r, mn_u, mx_u = lat.minmax()
+    assert (mn_r, mx_r, mn_u, mx_u) == (ref[1].min(), ref[1].max(), ref[2].min(), ref[2].max())
+    lat.close()
+
+
+def test_omega_change_after_a_multi_step_pass(P, oracle):
+    """experiments.py:171-180 sweeps omega over one resident state: the collision that ended the previous call is
+    redone with the new omega — after a multi-step pass by re-running it with a different omega for its last level."""
+    from lattice_boltzmann_parallel_solver_b200.engine import Lattice
+    shape = (2048, 512)
+    f, rho, u = random_state(oracle, shape, 91)
+    lat = Lattice(*shape)
+    lat.load(f, rho, u, 0.7)
+    lat.run(6, 0.7)                   # two three-step passes; the call ends on a pass
+    lat.run(5, 1.6)                   # redo of the last pass (levels 1-2 with 0.7, level 3 with 1.6), then 3 + 2
+    ref = oracle.c.run(f, rho, u, 0.7, oracle.c.periodic(), 6)
+    ref = oracle.c.run(*ref, 1.6, oracle.c.periodic(), 5)
+    for a, b, nm in zip(lat.fields(), ref, 'f rho u'.split()):
+        assert_parity(a, b, f'omega change {nm}')
+    lat.close()
 
 
 def _karman_bundle(P, shape, second_plate=False):
@@ -652,3 +733,5 @@ def test_options_and_state_errors(P, oracle):
         Lattice(0, 5)
     with pytest.raises(AssertionError):
         Lattice(64, 64, ghost=(2, 1))
+    with pytest.raises(AssertionError):
+        Lattice(64, 64, ghost=(5, 0))

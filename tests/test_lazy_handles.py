@@ -266,3 +266,68 @@ def test_old_handle_read_while_newer_steps_are_queued(L):
     assert np.array_equal(np.asarray(hist[9][0]), hist[9][1]) and lat.time == 10
     for h, want in hist:
         assert np.array_equal(np.asarray(h), want)
+
+
+def test_results_can_be_edited_in_place_like_the_reference_arrays(L):
+    """The reference hands back ordinary writable ndarrays: `f += x`, np.add(f, x, out=f) must work on a handle."""
+    f, rho, u = start(seed=11)
+    hf, hr, hu = L.lattice_boltzmann_step(f, rho, u, 1.0)
+    ref = [a.copy() for a in onp.step(f, rho, u, 1.0)]
+    keep = hf
+    hf += 0.25
+    assert hf is keep
+    ref[0] += 0.25
+    np.multiply(hr, 2.0, out=hr)
+    ref[1] *= 2.0
+    assert np.array_equal(np.asarray(hf), ref[0]) and np.array_equal(np.asarray(hr), ref[1])
+    assert not np.asarray(hu).flags.writeable            # documented: the plain host copy is read-only
+    nxt = L.lattice_boltzmann_step(hf, hr, hu, 1.0)      # edited handles are uploaded, not taken for the device state
+    exp = onp.step(ref[0], ref[1], ref[2], 1.0)
+    assert np.array_equal(np.asarray(nxt[0]), exp[0]) and np.array_equal(np.asarray(nxt[2]), exp[2])
+
+
+def test_a_sweep_does_not_pin_device_lattices(L):
+    """Every experiment of a sweep builds fresh closures (src/experiments.py:692-694, 759-761): identical scenarios
+    must reuse one device lattice, and lattices nobody reads from any more must be freed before new ones are made."""
+    for rep in range(3):                                  # same scenario three times: one context
+        f, rho, u = start((12, 10), seed=rep)
+        for _ in range(3):
+            f, rho, u = L.lattice_boltzmann_step(f, rho, u, 1.0)
+        assert np.array_equal(np.asarray(rho), _run_ref((12, 10), rep, 3)[1])
+    assert len(L.fake.ctxs) == 1
+    for n in range(13, 20):                               # a sweep over sizes: old lattices are retired
+        f, rho, u = start((n, 10), seed=n)
+        f, rho, u = L.lattice_boltzmann_step(f, rho, u, 1.0)
+        np.asarray(u)
+        del f, rho, u
+    assert len(L.fake.ctxs) <= L.MAX_IDLE_LATTICES + 1
+    # a lattice somebody still holds an unread result of is never retired behind their back
+    f, rho, u = start((30, 10), seed=1)
+    held = L.lattice_boltzmann_step(f, rho, u, 1.0)
+    for n in range(31, 36):
+        g = L.lattice_boltzmann_step(*start((n, 10), seed=n), 1.0)
+        np.asarray(g[0])
+        del g
+    assert np.array_equal(np.asarray(held[2]), onp.step(f, rho, u, 1.0)[2])
+
+
+def _run_ref(shape, seed, n):
+    s = start(shape, seed)
+    for _ in range(n):
+        s = onp.step(*s, 1.0)
+    return s
+
+
+def test_out_of_device_memory_retires_idle_lattices_and_retries(L):
+    real_create = L.fake.lbm_create
+
+    def create(device, nx, ny, gx, gy, bc, out):
+        if len(L.fake.ctxs) >= 2:
+            L.fake.err = b'cannot allocate'
+            return 4                                      # LBM_ERR_NOMEM
+        return real_create(device, nx, ny, gx, gy, bc, out)
+    L.fake.lbm_create = create
+    for n in (12, 13, 14, 15):
+        g = L.lattice_boltzmann_step(*start((n, 10), seed=n), 1.0)
+        assert np.array_equal(np.asarray(g[1]), _run_ref((n, 10), n, 1)[1])
+    assert len(L.fake.ctxs) <= 2
