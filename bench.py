@@ -104,18 +104,43 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------
-# CPU baseline: the oracle port of the reference's numpy algorithm (the reference itself is Python and does not
-# travel to the GPU box; oracle/lbm_numpy.py is pinned to it bit-for-bit by tests/test_oracle_golden.py)
+# CPU baseline: the reference's OWN numpy time step when its sources travelled with the repo (baseline/_ref/src, filled
+# by __graft_entry__.build() from /root/reference; kind "reference"), else the oracle port of it (oracle/lbm_numpy.py,
+# pinned to the reference bit for bit by tests/test_oracle_golden.py; kind "port")
 # ---------------------------------------------------------------------------------------------------------
-def cpu_reference_mlups(n, steps, warmup):
+REF_SRC = os.path.join(ROOT, 'baseline', '_ref', 'src')
+
+
+def cpu_modules():
+    """-> (step(f, rho, u, omega, boundary, comm), equilibrium(rho, u), kind)"""
+    if os.path.exists(os.path.join(REF_SRC, 'lattice_boltzmann_method.py')):
+        if REF_SRC not in sys.path:
+            sys.path.insert(0, REF_SRC)
+        import lattice_boltzmann_method as R          # the unmodified reference module (flat import, as its Makefile does)
+        assert os.path.dirname(os.path.abspath(R.__file__)) == REF_SRC
+        return R.lattice_boltzmann_step, R.equilibrium_distr_func, 'reference'
     from oracle import lbm_numpy as onp
-    rho, u = onp.sinusoidal_velocity_x((n, n), EPS)
-    f = onp.equilibrium(rho, u)
+    return onp.step, onp.equilibrium, 'port'
+
+
+def shear_wave(shape, ny_profile=None):
+    """rho = 1, u = (eps sin(2 pi y / ly), 0) — initial_values.py:67-93."""
+    ly = shape[1] if ny_profile is None else ny_profile
+    rho = np.ones(shape)
+    u = np.zeros(shape + (2,))
+    u[..., 0] = (EPS * np.sin(np.divide(2 * np.pi * np.arange(shape[1]), ly)))[None, :]
+    return rho, u
+
+
+def cpu_reference_mlups(n, steps, warmup):
+    step, equilibrium, _ = cpu_modules()
+    rho, u = shear_wave((n, n))
+    f = equilibrium(rho, u)
     for _ in range(warmup):
-        f, rho, u = onp.step(f, rho, u, OMEGA)
+        f, rho, u = step(f, rho, u, OMEGA)
     t0 = time.perf_counter()
     for _ in range(steps):
-        f, rho, u = onp.step(f, rho, u, OMEGA)
+        f, rho, u = step(f, rho, u, OMEGA)
     dt = time.perf_counter() - t0
     return n * n * steps / dt / 1e6, dt
 
@@ -125,15 +150,15 @@ def _cpu_worker(rank, k, n, steps, warmup, shm_name, barrier, out, check_name=No
     moments) on a slab of the n x n periodic shear-wave lattice; the four Sendrecv of parallelization_utils.py:34-49
     go through a shared-memory mailbox (there is no MPI in the image)."""
     from multiprocessing import shared_memory
-    from oracle import lbm_numpy as onp
+    step, equilibrium, _ = cpu_modules()
     os.environ['OMP_NUM_THREADS'] = '1'
     nloc = n // k
     shm = shared_memory.SharedMemory(name=shm_name)
     mail = np.ndarray((k, 2, n + 2, 9), dtype=np.float64, buffer=shm.buf)
-    rho, u = onp.sinusoidal_velocity_x((nloc + 2, n + 2), EPS)
+    rho, u = shear_wave((nloc + 2, n + 2))
     prof = EPS * np.sin(np.divide(2 * np.pi * ((np.arange(n + 2) - 1) % n), n))
     u[..., 0] = prof[None, :]
-    f = onp.equilibrium(rho, u)
+    f = equilibrium(rho, u)
     left, right = (rank - 1) % k, (rank + 1) % k
 
     def comm(fp):
@@ -148,11 +173,11 @@ def _cpu_worker(rank, k, n, steps, warmup, shm_name, barrier, out, check_name=No
         return fp
 
     for _ in range(warmup):
-        f, rho, u = onp.step(f, rho, u, OMEGA, None, comm)
+        f, rho, u = step(f, rho, u, OMEGA, None, comm)
     barrier.wait()
     t0 = time.perf_counter()
     for _ in range(steps):
-        f, rho, u = onp.step(f, rho, u, OMEGA, None, comm)
+        f, rho, u = step(f, rho, u, OMEGA, None, comm)
     barrier.wait()
     out[rank] = time.perf_counter() - t0
     if check_name:   # tests: gather the interiors so the decomposition can be compared with one process
@@ -208,7 +233,8 @@ def cpu_model():
 
 
 def run_reference(args, rank):
-    """--impl reference: the reference's CPU algorithm (oracle port of its numpy path, kind "port") on ALL host
+    """--impl reference: the reference's CPU implementation (its own lattice_boltzmann_step from baseline/_ref/src, kind
+    "reference"; the oracle port of it where the sources did not travel, kind "port") on ALL host
     cores: k = largest power of two <= cores processes, slab decomposition + ghost exchange as under mpirun -N k.
     Each step is a bounded sample of the workload: one time step of an n x n lattice (n = --cpu-size)."""
     if rank != 0:
@@ -229,7 +255,10 @@ def run_reference(args, rank):
         mlups, dt = cpu_reference_mlups_parallel(n, args.steps, args.warmup, k)
     else:
         mlups, dt = cpu_reference_mlups(n, args.steps, args.warmup)
-    sample = (f'{n}x{n} periodic shear wave (same fields/omega as the GPU arm, which runs {args.size}^2 per GPU; the '
+    kind = cpu_modules()[2]
+    impl_name = ("the reference's own lattice_boltzmann_step (baseline/_ref/src, unmodified)" if kind == 'reference' else
+                 'oracle/lbm_numpy.py (numpy restatement of the reference)')
+    sample = (f'{impl_name}: {n}x{n} periodic shear wave (same fields/omega as the GPU arm, which runs {args.size}^2 per GPU; the '
               f'numpy path needs ~400 B/cell so the full size does not fit/finish), {args.steps} steps after '
               f'{args.warmup} warm-up, {k} processes x 1 thread (numpy ufuncs are single-threaded; slabs + ghost-row '
               f'exchange through shared memory, as mpirun -N {k}); host: {host_cores()} usable cores, {cpu_model()}')
@@ -242,7 +271,7 @@ def run_reference(args, rank):
                                f'needs ~400 B/cell so the full size neither fits nor finishes)',
                    'lattice': [n, n], 'gpu_arm_lattice_per_gpu': [args.size, args.size], 'omega': OMEGA, 'epsilon': EPS,
                    'decomposition': f'{k} processes x 1 thread, slabs along the slow axis with a ghost ring'},
-        'cpu_baseline': {'value': mlups, 'unit': 'MLUPS', 'cores': k, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': {'value': mlups, 'unit': 'MLUPS', 'cores': k, 'kind': kind, 'sample': sample},
         'e2e': {'value': mlups, 'unit': 'MLUPS', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     emit(line)
@@ -576,9 +605,12 @@ def main():
         v, dt = (cpu_reference_mlups_parallel(args.cpu_size, steps_cpu, 1, k) if k > 1 else
                  cpu_reference_mlups(args.cpu_size, steps_cpu, 1))
         v1, dt1 = cpu_reference_mlups(args.cpu_size, 2, 1)
-        cpu = {'value': v, 'unit': 'MLUPS', 'cores': k, 'kind': 'port', 'single_core_value': v1,
+        kind = cpu_modules()[2]
+        impl_name = ("the reference's own lattice_boltzmann_step (baseline/_ref/src, unmodified)" if kind == 'reference' else
+                     'oracle/lbm_numpy.py (numpy restatement of the reference)')
+        cpu = {'value': v, 'unit': 'MLUPS', 'cores': k, 'kind': kind, 'single_core_value': v1,
                'sample': f'{args.cpu_size}x{args.cpu_size} periodic shear wave, {steps_cpu} steps after 1 warm-up, '
-                         f'oracle/lbm_numpy.py (numpy restatement of the reference) on {k} processes x 1 thread with '
+                         f'{impl_name} on {k} processes x 1 thread with '
                          f'slab decomposition + ghost-row exchange (as mpirun -N {k}); host: {host_cores()} usable '
                          f'cores, {cpu_model()}; {dt:.1f} s; one process alone: {v1:.2f} MLUPS'}
     ref_cfg = None

@@ -1,6 +1,8 @@
-"""A CPU stand-in for liblbm_b200.so, for TESTS of the host-side handle logic only (engine.py, the lazy results of
-lattice_boltzmann_step). It implements the subset of include/lbm_b200.h that a periodic, boundary-free lattice
-needs, with the oracle as its arithmetic. It is never importable from the product package."""
+"""A CPU stand-in for liblbm_b200.so, for TESTS of the host-side logic only (engine.py, the lazy results of
+lattice_boltzmann_step, the reference's own drivers running on the drop-in modules without a GPU). It implements the
+subset of include/lbm_b200.h those tests reach — stateless operators, contexts with the kind-rule boundary description
+(pull / bounce [- K] / constant / outlet; no pressure-periodic flags) and a self-periodic ghost ring — with the oracle
+as its arithmetic. It is never importable from the product package."""
 import ctypes as C
 
 import numpy as np
@@ -12,9 +14,14 @@ def _arr(ptr, shape):
     return np.ctypeslib.as_array(ptr, shape=shape) if ptr else None
 
 
+OPP = (0, 3, 4, 1, 2, 7, 8, 5, 6)
+
+
 class _Ctx:
-    def __init__(self, nx, ny):
+    def __init__(self, nx, ny, ghost=(0, 0), bc=None):
         self.nx, self.ny = nx, ny
+        self.ghost = ghost
+        self.bc = bc             # None or dict(kind_map, kinds, ktab, ctab)
         self.state = None        # (f, rho, u) of the current time, reference semantics
         self.t = 0
         self.launches = 0
@@ -38,12 +45,78 @@ class FakeLib:
         return self.err
 
     def lbm_create(self, device, nx, ny, gx, gy, bc, out):
-        assert not bc, 'the fake only knows boundary-free lattices'
+        desc = None
+        if bc:
+            d = bc._obj
+            kinds = [(tuple(d.kinds[k].rule), int(d.kinds[k].flags), int(d.kinds[k].skip_store)) for k in range(d.n_kinds)]
+            assert all(fl & ~1 == 0 and sk == 0 for _, fl, sk in kinds), 'the fake has no pressure-periodic boundary'
+            desc = {'kind_map': np.array(np.ctypeslib.as_array(d.kind_map, shape=(nx, ny))),
+                    'kinds': kinds,
+                    'ktab': np.array(np.ctypeslib.as_array(d.k_table, shape=(d.n_k_rows, 9))),
+                    'ctab': np.array(np.ctypeslib.as_array(d.c_table, shape=(d.n_c_rows, 9))) if d.n_c_rows else np.zeros((0, 9))}
         h = self.next
         self.next += 1
-        self.ctxs[h] = _Ctx(nx, ny)
+        self.ctxs[h] = _Ctx(nx, ny, (gx, gy), desc)
         out._obj.value = h
         return 0
+
+    # -- halo: one rank, every neighbour is the lattice itself (communication() with a 1x1 topology) ------------------
+    def lbm_halo_export_handle(self, ctx, out):
+        return 0
+
+    def lbm_halo_connect(self, ctx, slot, peer):
+        return 0
+
+    def lbm_halo_finalize(self, ctx):
+        return 0
+
+    # -- stateless operators -------------------------------------------------------------------------------------
+    def lbm_equilibrium(self, device, n, rho, u, out):
+        _arr(out, (n, 9))[...] = onp.equilibrium(_arr(rho, (n,)), _arr(u, (n, 2)))
+        return 0
+
+    def lbm_density(self, device, n, f, out):
+        _arr(out, (n,))[...] = onp.density(_arr(f, (n, 9)))
+        return 0
+
+    def lbm_velocity(self, device, n, rho, f, out):
+        _arr(out, (n, 2))[...] = onp.velocity(_arr(rho, (n,)), _arr(f, (n, 9)))
+        return 0
+
+    def lbm_streaming(self, device, nx, ny, f, out):
+        _arr(out, (nx, ny, 9))[...] = onp.stream(_arr(f, (nx, ny, 9)))
+        return 0
+
+    def _one_step(self, c, omega):
+        """collide with the given moments -> ghost exchange -> stream -> kind rules -> moments
+        (src/lattice_boltzmann_method.py:213-226 with the closures' overwrites as data, include/lbm_b200.h)."""
+        f, rho, u = c.state
+        if c.bc is None and c.ghost == (0, 0):
+            return onp.step(f, rho, u, omega)
+        f_pre = onp.collide(f, rho, u, omega)
+        if c.ghost != (0, 0):
+            assert c.ghost == (1, 1)
+            f_pre = onp.self_exchange(f_pre)
+        f_post = onp.stream(f_pre)
+        if c.bc is not None:
+            km = c.bc['kind_map']
+            for k, (rules, flags, skip) in enumerate(c.bc['kinds']):
+                if k == 0:
+                    continue
+                cells = km == k
+                if not cells.any():
+                    continue
+                for i, r in enumerate(rules):
+                    typ, row = r & 7, r >> 3
+                    if typ == 1:      # bounce: f_post[i] = f_pre[opp i] - K[row][opp i]
+                        f_post[cells, i] = np.subtract(f_pre[cells, OPP[i]], c.bc['ktab'][row][OPP[i]]) if row else f_pre[cells, OPP[i]]
+                    elif typ == 2:    # inlet constants
+                        f_post[cells, i] = c.bc['ctab'][row][i]
+                    elif typ == 3:    # outlet: the step's input f of the row before
+                        xs, ys = np.nonzero(cells)
+                        f_post[xs, ys, i] = f[xs - 1, ys, i]
+        rho2 = onp.density(f_post)
+        return f_post, rho2, onp.velocity(rho2, f_post)
 
     def _c(self, ctx):
         return self.ctxs[ctx.value if hasattr(ctx, 'value') else ctx]
@@ -84,7 +157,7 @@ class FakeLib:
             return 3
         c.calls.append(('step', n))
         for _ in range(n):
-            c.state = onp.step(*c.state, omega)
+            c.state = self._one_step(c, omega)
             c.t += 1
             c.launches += 1
             c.steps_log.append(omega)

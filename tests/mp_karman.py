@@ -4,6 +4,8 @@ checks its whole local arrays (ghost ring included) against what the reference p
 ranks (tests/golden/karman_ranks.npz); rank 0 additionally checks the save_mpiio gather against the serial run.
 
 GPU box:  torchrun --nproc-per-node K tests/mp_karman.py          (NCCL process group, CUDA-IPC halo)
+          torchrun --nproc-per-node K tests/mp_karman.py --shared-gpu   (K processes on ONE GPU: the same CUDA-IPC peer
+          stores and flag handshake between processes, kernels time-sliced; gloo process group)
 CPU box:  torchrun --nproc-per-node K tests/mp_karman.py --host   (gloo; host-side logic only: the time step is
           done by the ORACLE here — tests may — while topology, bundles, CartComm.Sendrecv and save_mpiio are ours)
 """
@@ -24,10 +26,11 @@ def sha(a):
 
 def main():
     host = '--host' in sys.argv
-    from lattice_boltzmann_parallel_solver_b200 import dist as ldist
+    shared = '--shared-gpu' in sys.argv      # all ranks on ONE GPU (CUDA-IPC between processes, time-sliced kernels):
+    from lattice_boltzmann_parallel_solver_b200 import dist as ldist   # NCCL refuses two ranks per device -> gloo plumbing
     from lattice_boltzmann_parallel_solver_b200 import parallelization_utils as PU
     from oracle import lbm_numpy as onp
-    ldist.ensure_process_group('gloo' if host else 'nccl')
+    ldist.ensure_process_group('gloo' if host or shared else 'nccl')
     comm = ldist.comm_world()
     size, rank = comm.Get_size(), comm.Get_rank()
     g = np.load(os.path.join(ROOT, 'tests', 'golden', 'karman_ranks.npz'))
@@ -74,7 +77,7 @@ def main():
         F = np.stack([np.load(os.path.join(tmp, f'f_{j}.npy')) for j in range(9)], axis=-1)
         assert F.shape == (lx, ly, 9)
         assert sha(F) == str(g['serial_f11']), 'gathered populations differ from the serial run'
-        print(f'OK {size} ranks ({"host/gloo" if host else "gpu/nccl+ipc"})', flush=True)
+        print(f'OK {size} ranks ({"host/gloo" if host else ("one gpu/gloo+ipc" if shared else "gpu/nccl+ipc")})', flush=True)
     comm.Barrier()
     if not host:
         from lattice_boltzmann_parallel_solver_b200 import lattice_boltzmann_method as L

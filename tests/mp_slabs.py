@@ -4,7 +4,9 @@
                                                   (run with CUDA_DEVICE_MAX_CONNECTIONS=32: a kernel of one slab
                                                   spins on flags of kernels of other slabs enqueued later, so their
                                                   streams must not share a hardware queue)
-    torchrun --nproc-per-node K tests/mp_slabs.py one process per GPU, CUDA-IPC halo (the real thing)
+    torchrun --nproc-per-node K tests/mp_slabs.py [--depth D] [--shared-gpu]
+                                                  one process per GPU, CUDA-IPC halo (the real thing); D ghost rows and
+                                                  D steps per pass; --shared-gpu: all processes on GPU 0 (gloo plumbing)
 """
 import os
 import sys
@@ -30,16 +32,16 @@ def main():
     f = onp.equilibrium(rho, u)
     ref = lbm_c.run(f, rho, u, omega, lbm_c.periodic(), steps)
 
-    def padded(a, c):
-        return np.ascontiguousarray(a[np.arange(c * n - 2, (c + 1) * n + 2) % nx])
+    def padded(a, c, g=2):
+        return np.ascontiguousarray(a[np.arange(c * n - g, (c + 1) * n + g) % nx])
 
-    def check(lat, c):
-        got = lat.fields(region=(2, n + 2, 0, ny))
+    def check(lat, c, g=2):
+        got = lat.fields(region=(g, n + g, 0, ny))
         for a, b, nm in zip(got, ref, 'f rho u'.split()):
             assert np.array_equal(a, b[c * n:(c + 1) * n]), f'slab {c}: {nm} differs from the single-block oracle'
         try:
-            lat.fields(region=(0, n + 4, 0, ny))
-            raise SystemExit('ghost rows of a two-row slab must not be materialisable')
+            lat.fields(region=(0, n + 2 * g, 0, ny))
+            raise SystemExit('ghost rows of a slab must not be materialisable')
         except AssertionError:
             pass
 
@@ -70,22 +72,26 @@ def main():
     else:
         from lattice_boltzmann_parallel_solver_b200 import dist as ldist
         from lattice_boltzmann_parallel_solver_b200 import parallelization_utils as PU
-        ldist.ensure_process_group('nccl')
+        shared = '--shared-gpu' in sys.argv      # all ranks on one GPU: gloo plumbing, CUDA-IPC between the processes
+        depth = int(sys.argv[sys.argv.index('--depth') + 1]) if '--depth' in sys.argv else 2
+        ldist.ensure_process_group('gloo' if shared else 'nccl')
         comm = ldist.comm_world()
         rank = comm.Get_rank()
-        N.set_device(int(os.environ.get('LOCAL_RANK', '0')))
-        lat = Lattice(n + 4, ny, ghost=(2, 0))
+        N.set_device(0 if shared else int(os.environ.get('LOCAL_RANK', '0')))
+        g = depth
+        lat = Lattice(n + 2 * g, ny, ghost=(g, 0))
+        lat.set_option('fused_depth', depth)
         halo = PU.communication(comm.Create_cart(dims=[k, 1], periods=[True, True]))
         halo.attach(lat)
-        lat.load(padded(f, rank), padded(rho, rank), padded(u, rank), omega)
+        lat.load(padded(f, rank, g), padded(rho, rank, g), padded(u, rank, g), omega)
         comm.Barrier()
-        for chunk in (9, 4):
+        for chunk in (7, 6):              # 7: passes + a one-step launch; 6: ends on a pass (FINAL-mode materialisation)
             lat.run(chunk)
         lat.sync()
-        check(lat, rank)
+        check(lat, rank, g)
         comm.Barrier()
         if rank == 0:
-            print(f'OK {k} slabs, one process per GPU', flush=True)
+            print(f'OK {k} slabs, one process per GPU' + (' (shared)' if shared else '') + f', depth {depth}', flush=True)
         lat.close()
 
 

@@ -1,0 +1,102 @@
+"""Runs the REFERENCE's own, unmodified drivers (src/experiments.py, src/main.py; copied to baseline/_ref/src by
+`__graft_entry__.build()`) and dumps what they produced, in one of three configurations:
+
+    python tests/ref_drivers.py reference <out.npz>   everything from the reference (its numpy time step): the expectation
+    python tests/ref_drivers.py fake      <out.npz>   this package's drop-in modules on tests/fake_native.py (CPU)
+    python tests/ref_drivers.py gpu       <out.npz>   this package's drop-in modules on the CUDA library
+
+matplotlib / pygifsicle are test stubs (tests/stubs); mpi4py is the package's single-process stand-in. The drivers run
+in a scratch directory with the `figures/` tree they write into. Own process: the flat module names (`experiments`,
+`lattice_boltzmann_method`, ...) must not leak into the test session.
+"""
+import contextlib
+import io
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, 'lattice_boltzmann_parallel_solver_b200')
+
+
+def ref_src():
+    for cand in (os.path.join(ROOT, 'baseline', '_ref', 'src'), '/root/reference/src'):
+        if os.path.exists(os.path.join(cand, 'experiments.py')):
+            return cand
+    return None
+
+
+def main():
+    mode, out = sys.argv[1], sys.argv[2]
+    src = ref_src()
+    assert src, 'reference drivers not available (baseline/_ref/src is filled by __graft_entry__.build())'
+    stubs, dropin = os.path.join(ROOT, 'tests', 'stubs'), os.path.join(PKG, 'dropin')
+    # reference: its own modules first (dropin only supplies `mpi4py`); ours: the drop-in modules shadow the reference's
+    sys.path[:0] = [src, stubs, dropin, ROOT] if mode == 'reference' else [dropin, stubs, src, ROOT]
+    if mode == 'fake':
+        from lattice_boltzmann_parallel_solver_b200 import _native as N
+        from tests.fake_native import FakeLib
+        fake = FakeLib()
+        N.load = lambda: fake
+        N.device = lambda: 0
+    work = tempfile.mkdtemp(prefix='lbm_ref_drivers_')
+    for d in ('shear_wave_decay', 'couette_flow', 'poiseuille_flow', 'von_karman_vortex_shedding/reynold_strouhal',
+              'von_karman_vortex_shedding/nx_strouhal', 'von_karman_vortex_shedding/blockage_strouhal',
+              'von_karman_vortex_shedding/scaling_test', 'von_karman_vortex_shedding/all_png_parallel'):
+        os.makedirs(os.path.join(work, 'figures', d))
+    os.chdir(work)
+    import matplotlib
+    import experiments as E
+    import lattice_boltzmann_method as L
+    where = os.path.dirname(os.path.abspath(L.__file__))
+    assert where == (src if mode == 'reference' else dropin), f'wrong lattice_boltzmann_method on the path: {where}'
+    res = {}
+    quiet = contextlib.redirect_stderr(io.StringIO())   # tqdm bars
+
+    def plotted(prefix):
+        return [a for name, a, k in matplotlib.calls if name.startswith(prefix)]
+
+    with quiet:
+        # (1) shear-wave viscosity vs omega: whole-field np.amin / np.amax after EVERY step, omega sweep over one initial
+        #     state (src/experiments.py:147-223)
+        matplotlib.calls.clear()
+        E.plot_measured_viscosity_vs_omega(lattice_grid_shape=(24, 20), time_steps=260, omega_discretization=3)
+        curves = [a for a in plotted('plt.subplots()[') if len(a) == 2]
+        for i, (x, y) in enumerate(curves):
+            res[f'visc_{i}_x'], res[f'visc_{i}_y'] = np.asarray(x, dtype=float), np.asarray(y, dtype=float)
+        assert len(curves) == 4, len(curves)
+        # (2) Couette: moving wall + rigid wall, profile + linear regression written to csv (:304-374)
+        matplotlib.calls.clear()
+        E.plot_couette_flow_vel_vectors(lattice_grid_shape=(12, 14), omega=1.0, U=0.05, time_steps=150)
+        res['couette_csv'] = np.genfromtxt('figures/couette_flow/linregress.csv', delimiter=',', skip_header=1)
+        res['couette_profile'] = np.asarray(plotted('plt.plot')[0][0], dtype=float)
+        # (3) x_strouhal: parallel von Karman path on one rank, one velocity cell read after every step (:650-720)
+        E.x_strouhal('reynold_strouhal', lattice_grid_shape=(60, 36), plate_size=10, time_steps=90)
+        res['vel_at_p'] = np.load('figures/von_karman_vortex_shedding/reynold_strouhal/vel_at_p_25.npy')
+        # (4) scaling_test: the reference's published benchmark loop (:723-774)
+        E.scaling_test('scaling_test', lattice_grid_shape=(60, 36), plate_size=10, time_steps=70)
+        res['scaling_mlups_finite'] = np.array([float(np.isfinite(np.load(
+            'figures/von_karman_vortex_shedding/scaling_test/60_36_1.npy')[0]))])
+        # (5) velocity evolution: keeps results of many steps and looks at them after the loop (:102-144)
+        matplotlib.calls.clear()
+        E.plot_evolution_of_velocity(lattice_grid_shape=(20, 16), epsilon=0.05, omega=1.2, time_steps=100, number_of_visualizations=10)
+        lines = [a for a in plotted('plt.subplots()[') if len(a) >= 2 and np.ndim(a[1]) == 1 and len(a[1]) == 16]
+        res['evolution_lines'] = np.array([np.asarray(a[1], dtype=float) for a in lines])
+    # (6) main.py end to end (argparse -> experiments): couette_vectors with explicit sizes
+    matplotlib.calls.clear()
+    sys.argv = ['main.py', '-f', 'couette_vectors', '-l', '10', '12', '-t', '60', '-mwv', '0.03']
+    import main as M
+    with quiet:
+        M.main()
+    res['main_couette_csv'] = np.genfromtxt('figures/couette_flow/linregress.csv', delimiter=',', skip_header=1)
+    if mode != 'reference':
+        from lattice_boltzmann_parallel_solver_b200 import lattice_boltzmann_method as impl
+        impl.release_lattices()
+    np.savez(out, **res)
+    print('OK', mode, sorted(res), flush=True)
+
+
+if __name__ == '__main__':
+    main()

@@ -512,6 +512,22 @@ def test_full_size_16384_rows_equal_thin_lattice(P, oracle):
     lat.close()
 
 
+def test_full_size_16384_x_periodic_field_default_geometry(P):
+    """The headline launch geometry (default depth and segment length at 16384^2) on a field that varies along BOTH
+    axes: rho(x) with period 64 on top of the shear wave, so that the solution equals a 64 x 16384 lattice the C
+    oracle runs in a second (the same job bench.py runs at every N and reports as `parity`). A row mix-up inside a
+    segment, a wrong ring slot or a wrong column shift cannot hide here."""
+    import bench
+    from lattice_boltzmann_parallel_solver_b200.engine import Lattice
+    n = 16384
+    prof = 0.01 * np.sin(np.divide(2 * np.pi * np.arange(n), n))
+    lat = Lattice(n, n)
+    for steps in (12, 13):            # ends on a three-step pass / on a one-step launch
+        res = bench.run_parity(lat, 1, 0, n, n, prof, steps, lambda: None, lambda v: v, lambda v: v)
+        assert res['mismatches'] == 0 and res['rows'] == 12, res
+    lat.close()
+
+
 # ---------------------------------------------------------------------------------------------------------
 # two steps per pass (temporal blocking) == two one-step passes
 # ---------------------------------------------------------------------------------------------------------

@@ -265,8 +265,8 @@ def test_dropin_modules_expose_the_reference_api():
 
 
 def test_cpu_baseline_processes_equal_one_process():
-    """bench.py's all-cores CPU arm (k processes, slabs, shared-memory ghost exchange) computes exactly what the
-    single-process oracle computes."""
+    """bench.py's all-cores CPU arm (k processes, slabs, shared-memory ghost exchange; the reference's own time step
+    where baseline/_ref/src exists, else the oracle port) computes exactly what the single-process oracle computes."""
     sys.path.insert(0, ROOT)
     import bench
     from oracle import lbm_numpy as onp
@@ -282,7 +282,10 @@ def test_cpu_baseline_processes_equal_one_process():
     assert line.returncode == 0, line.stderr[-2000:]
     assert len(line.stdout.strip().splitlines()) == 1, 'bench.py must print exactly one line on stdout'
     d = json.loads(line.stdout.strip().splitlines()[-1])
-    assert d['impl'] == 'reference' and d['value'] > 0 and d['cpu_baseline']['kind'] == 'port' and d['e2e']['value'] == d['value']
+    have_ref = os.path.exists(os.path.join(ROOT, 'baseline', '_ref', 'src', 'lattice_boltzmann_method.py'))
+    assert d['impl'] == 'reference' and d['value'] > 0 and d['e2e']['value'] == d['value']
+    assert d['cpu_baseline']['kind'] == ('reference' if have_ref else 'port')      # the unmodified reference where it travelled
+    assert d['config']['lattice'] == [256, 256] and '256x256' in d['config']['workload']   # states its OWN workload
 
 
 # ---------------------------------------------------------------------------------------------------------
