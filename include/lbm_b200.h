@@ -123,27 +123,38 @@ enum {
     LBM_BC_EDGE = 2       /* mask-free periodic kernel over all cells + thin fix-up kernel over the non-fluid cells */
 };
 
-/* ghost_x: 0 (periodic wrap in-kernel), 1 (the reference's ghost ring) or 2 (two-row slabs of a fluid lattice for
- * the two-steps-per-pass kernel; needs ghost_y = 0 and no boundary description); ghost_y: 0 or 1. */
+/* ghost_x: 0 (periodic wrap in-kernel), 1 (the reference's ghost ring) or 2..4 (slabs of a fluid lattice for the
+ * multi-step kernel: g ghost rows per side supply the dependency cone of a g-step pass; needs ghost_y = 0 and no
+ * boundary description); ghost_y: 0 or 1. */
 int lbm_create(int device, int nx, int ny, int ghost_x, int ghost_y, const lbm_bc_desc *bc /* may be NULL */,
                lbm_ctx **out);
 int lbm_destroy(lbm_ctx *ctx);
 int lbm_set_bc_mode(lbm_ctx *ctx, int mode);
-/* Scheduling switches for A/B measurements (all default to 1 except generic_kernel):
- *   "fused"          two time steps per pass on bandwidth-bound lattices (temporal blocking); on lattices with
- *                    boundary cells the rows whose two-step dependency cone is all fluid take the two-step kernel,
- *                    the other rows two one-step mask launches through a strip window (needs ghost_x = ghost_y = 0,
- *                    no pressure-periodic rows, and boundary cells on at most half of the rows)
- *   "graphs"         CUDA-graph replay of 32 captured steps on launch-bound lattices
- *   "pdl"            programmatic dependent launch between the step kernels of launch-bound lattices: the next step's
+/* Scheduling switches (A/B measurements, tests):
+ *   "fused"          (1) several time steps per pass on bandwidth-bound lattices (temporal blocking): fluid lattices take
+ *                    "fused_depth" steps per launch of k_stepNx; on lattices with boundary cells the rows whose two-step
+ *                    dependency cone is all fluid take the two-step kernel, the other rows two one-step mask launches
+ *                    through a strip window (needs ghost_x = ghost_y = 0, no pressure-periodic rows, and boundary cells
+ *                    on at most half of the rows)
+ *   "fused_depth"    (3) time steps per pass, 2..4; slabs are limited to their number of ghost rows. A call of n steps is
+ *                    n / depth passes, then one pass of the remainder (2 steps: the two-step kernel) or a one-step launch
+ *   "deep2"          (0) two-step passes through k_stepNx<2> instead of k_step2x
+ *   "graphs"         (1) CUDA-graph replay of 32 captured steps on launch-bound lattices
+ *   "pdl"            (1) programmatic dependent launch between the step kernels of launch-bound lattices: the next step's
  *                    blocks are launched and read their parameters / kind bytes while the current step still runs
- *   "generic_kernel" force the one-cell-per-thread step kernel
- *   "fused_exact"    (default 0) an even lbm_step(n) is exactly n/2 two-step passes without the one-step tail that
- *                    normally ends every call; results cannot be materialised until one more single step is taken
- *   "l2_prefetch"    (default 2) rows ahead of its march whose source segments the two-step kernel prefetches into
- *                    L2 with cp.async.bulk.prefetch; 0 = off
- *   "fused_seg"      output rows per thread block of the two-step kernel (default 0: 8..64 by lattice size)
- * Environment overrides at lbm_create: LBM_NO_FUSED=1, LBM_NO_GRAPHS=1, LBM_GENERIC_KERNEL=1, LBM_FUSED_SEG=n. */
+ *   "generic_kernel" (0) force the one-cell-per-thread step kernel
+ *   "fused_exact"    (0) lattices WITH boundary cells normally end every call with a one-step launch, so that the other
+ *                    buffer holds S_{t-1} for materialisation; 1 = no such tail (results cannot be materialised until one
+ *                    more single step is taken). Fluid lattices never need the tail: after a call that ended on a
+ *                    d-step pass, results are materialised by re-running that pass with its last level writing
+ *                    f_post / rho / u instead of colliding, and a changed omega redoes the pass's last collision.
+ *   "l2_prefetch"    (2) rows ahead of its march whose source segments the multi-step kernel prefetches into L2 with
+ *                    cp.async.bulk.prefetch; 0 = off
+ *   "fused_seg"      (0) output rows per thread block of the multi-step kernel; 0 = 8..256 by lattice size
+ *   "max_queued_calls" (4) lbm_step call k first waits for call k-4 to finish on the device (bounded host run-ahead:
+ *                    a driver loop that never reads a result cannot stop its clock with the GPU far behind); 0 = unbounded
+ * Environment overrides at lbm_create: LBM_NO_FUSED=1, LBM_NO_GRAPHS=1, LBM_GENERIC_KERNEL=1, LBM_FUSED_SEG=n,
+ * LBM_FUSED_DEPTH=d, LBM_DEEP2=1. */
 int lbm_set_option(lbm_ctx *ctx, const char *name, int value);
 /* bytes of device memory the context holds */
 int64_t lbm_device_bytes(const lbm_ctx *ctx);

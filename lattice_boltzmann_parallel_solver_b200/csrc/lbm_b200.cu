@@ -415,17 +415,6 @@ __device__ __forceinline__ void finish_cell(const StepParams &P, int x, int y, c
     }
 }
 
-// A non-fluid cell. Everything is inlined with compile-time population indices: the first version called an
-// out-of-line rule interpreter through an array reference, which put f[9] of EVERY cell in local memory and
-// doubled the DRAM writes of the mask kernel (profiles/r01_summary.md).
-template <bool HALO, bool FINAL>
-__device__ __forceinline__ void rule_cell(const StepParams &P, int x, int y, const lbm_kind &k)
-{
-    double f[9];
-    pull_rules(P, k, x, y, f);
-    finish_cell<HALO, FINAL>(P, x, y, f, k.flags, k.skip_store);
-}
-
 // Programmatic dependent launch (launch-bound lattices, where a step is ~1 us of work behind ~1 us of launch
 // latency): a step kernel releases its dependents at once, so the next step's blocks are launched, read their
 // parameters and their kind byte while this step still runs, and then wait here for this grid to complete and
@@ -433,28 +422,33 @@ __device__ __forceinline__ void rule_cell(const StepParams &P, int x, int y, con
 __device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-// One cell of one step (or of a materialisation): rule path or plain pulls -> finish_cell
+// One cell of one step (or of a materialisation). Only the nine PULLS differ between a fluid cell and a non-fluid
+// one (rule table, compile-time population indices: everything stays in registers); moments, collision and stores are
+// one common instruction stream. (The first version sent non-fluid cells through their own copy of the whole cell
+// update: a warp that holds a wall cell — two of the four warps of every Couette row — then ran the update twice, and
+// config 2 cost 4.35 us per step against 2.0 us for the periodic lattice of config 1, profiles/r01_summary.md section 12.)
 template <bool HALO, bool FINAL>
 __device__ __forceinline__ void step_cell(const StepParams &P, int x, int y, unsigned kind, const lbm_kind &k)
 {
+    double f[9];
+    unsigned flags = 0, skip = 0;
     if (kind != 0) {
-        rule_cell<HALO, FINAL>(P, x, y, k);
-    } else {
-        double f[9];
-        if (FINAL && P.use_snap) {
-            constexpr int cx[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1}, cy[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
+        pull_rules(P, k, x, y, f);
+        flags = k.flags;
+        skip = k.skip_store;
+    } else if (FINAL && P.use_snap) {
+        constexpr int cx[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1}, cy[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
 #pragma unroll
-            for (int i = 0; i < 9; i++) {
-                int xs = x - cx[i], ys = y - cy[i];
-                xs = xs < 0 ? P.NX - 1 : (xs >= P.NX ? 0 : xs);
-                ys = ys < 0 ? P.NY - 1 : (ys >= P.NY ? 0 : ys);
-                f[i] = ld_cell(P, i, xs, ys);
-            }
-        } else {
-            pull_fluid(P, x, y, f);
+        for (int i = 0; i < 9; i++) {
+            int xs = x - cx[i], ys = y - cy[i];
+            xs = xs < 0 ? P.NX - 1 : (xs >= P.NX ? 0 : xs);
+            ys = ys < 0 ? P.NY - 1 : (ys >= P.NY ? 0 : ys);
+            f[i] = ld_cell(P, i, xs, ys);
         }
-        finish_cell<HALO, FINAL>(P, x, y, f, 0u, 0u);
+    } else {
+        pull_fluid(P, x, y, f);
     }
+    finish_cell<HALO, FINAL>(P, x, y, f, flags, skip);
 }
 
 template <bool MASK, bool HALO, bool FINAL, bool LIST>
@@ -1375,6 +1369,14 @@ struct lbm_ctx {
     bool halo_ready = false, any_remote = false;
     cudaStream_t stream = nullptr, stream_edge = nullptr;
     cudaEvent_t ev_main = nullptr, ev_edge = nullptr;
+    // Bounded run-ahead of the host (option "max_queued_calls", default 4): lbm_step call k first waits until call
+    // k - max_queued_calls has finished on the device. A driver that never looks at a result inside its loop (the
+    // reference's scaling_test stops its clock right after the loop, src/experiments.py:763-769) then cannot run more
+    // than a few batches ahead of the GPU, so its wall clock covers the work it claims.
+    static const int kCallRing = 16;
+    cudaEvent_t ev_call[kCallRing] = {};
+    long long n_calls = 0;
+    int max_queued_calls = 4;
 };
 
 static void drop_graphs(lbm_ctx *c);
@@ -1638,6 +1640,8 @@ extern "C" int lbm_destroy(lbm_ctx *c)
     if (c->probe) cudaFreeHost(c->probe);
     if (c->progress) cudaFreeHost(c->progress);
     if (c->err_host) cudaFreeHost(c->err_host);
+    for (cudaEvent_t e : c->ev_call)
+        if (e) cudaEventDestroy(e);
     if (c->ev_main) cudaEventDestroy(c->ev_main);
     if (c->ev_edge) cudaEventDestroy(c->ev_edge);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -1736,6 +1740,7 @@ static int ctx_build(lbm_ctx *c, const lbm_bc_desc *bc)
     CK(cudaStreamCreateWithPriority(&c->stream_edge, cudaStreamNonBlocking, hi));
     CK(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_edge, cudaEventDisableTiming));
+    for (cudaEvent_t &e : c->ev_call) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     {
         const int smem = 4 * 6 * 2 * kFusedThreads * (int)sizeof(double);
         CK(cudaFuncSetAttribute(k_step2x<kFusedThreads, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1905,6 +1910,9 @@ extern "C" int lbm_set_option(lbm_ctx *c, const char *name, int value)
     else if (n == "l2_prefetch") {
         if (value < 0 || value > 8) return fail(LBM_ERR_ARG, "lbm_set_option: l2_prefetch must be 0..8 rows");
         c->l2_prefetch = value;
+    } else if (n == "max_queued_calls") {
+        if (value < 0 || value >= lbm_ctx::kCallRing) return fail(LBM_ERR_ARG, "lbm_set_option: max_queued_calls must be 0 (unbounded) .. %d", lbm_ctx::kCallRing - 1);
+        c->max_queued_calls = value;
     } else if (n == "fused_depth") {
         if (value < 2 || value > kMaxDepth) return fail(LBM_ERR_ARG, "lbm_set_option: fused_depth must be 2..%d", kMaxDepth);
         c->fused_depth = value;
@@ -1914,7 +1922,7 @@ extern "C" int lbm_set_option(lbm_ctx *c, const char *name, int value)
         if (value < 2 && value != 0) return fail(LBM_ERR_ARG, "lbm_set_option: fused_seg must be >= 2, or 0 for the default");
         c->fused_seg = value;
     } else
-        return fail(LBM_ERR_ARG, "lbm_set_option: unknown option '%s' (fused, graphs, pdl, generic_kernel, fused_exact, fused_seg, fused_depth, deep2, l2_prefetch)", name);
+        return fail(LBM_ERR_ARG, "lbm_set_option: unknown option '%s' (fused, graphs, pdl, generic_kernel, fused_exact, fused_seg, fused_depth, deep2, l2_prefetch, max_queued_calls)", name);
     return LBM_OK;
 }
 
@@ -2437,6 +2445,8 @@ extern "C" int lbm_step(lbm_ctx *c, double omega, int n_steps)
     if (n_steps == 0) return LBM_OK;
     if (int rc = async_error(c, "lbm_step")) return rc;
     CK(cudaSetDevice(c->device));
+    if (c->max_queued_calls > 0 && c->n_calls >= c->max_queued_calls)
+        CK(cudaEventSynchronize(c->ev_call[(c->n_calls - c->max_queued_calls) % lbm_ctx::kCallRing]));
     if (omega != c->omega) {
         // S[cur] was collided with the previous call's omega. Redo that collision from the retained S_{t-d}: the last
         // launch again (a one-step launch, or a multi-step pass whose LAST level collides with the new omega).
@@ -2486,6 +2496,8 @@ extern "C" int lbm_step(lbm_ctx *c, double omega, int n_steps)
         c->t++;
         c->last_depth = 1;
     }
+    CK(cudaEventRecord(c->ev_call[c->n_calls % lbm_ctx::kCallRing], c->stream));
+    c->n_calls++;
     return LBM_OK;
 }
 

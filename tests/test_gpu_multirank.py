@@ -132,7 +132,7 @@ def test_two_row_slabs_two_steps_per_pass():
     assert 'OK 4 slabs in one process' in res.stdout
 
 
-def _torchrun(script, size, port, *args, timeout=600, halo_timeout='60'):
+def _torchrun(script, size, port, *args, timeout=900, halo_timeout='120'):
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={size}',
            '--master-addr', '127.0.0.1', '--master-port', str(port), os.path.join(ROOT, 'tests', script)] + list(args)
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT,
@@ -141,40 +141,30 @@ def _torchrun(script, size, port, *args, timeout=600, halo_timeout='60'):
     return res.stdout
 
 
-@pytest.mark.parametrize('depth', [2, 3])
-def test_cross_process_slabs_on_one_gpu(depth):
-    """The real multi-process halo path — cudaIpcOpenMemHandle mappings, peer ghost stores from inside the multi-step
-    kernel, the flag handshake between PROCESSES — on a box with a single GPU: two ranks share device 0 (their kernels
-    are time-sliced, so a kernel that waits for the other rank's flag is eventually preempted; generous timeout).
-    Values must equal the single-block C oracle on a field that varies along the slab axis."""
-    out = _torchrun('mp_slabs.py', 2, 29560 + depth, '--shared-gpu', '--depth', str(depth))
-    assert f'OK 2 slabs, one process per GPU (shared), depth {depth}' in out
+def _placement(size):
+    """One process per GPU where the box has `size` GPUs (NCCL plumbing); otherwise ALL ranks on GPU 0 (gloo plumbing):
+    the same cudaIpcOpenMemHandle mappings, peer ghost stores from inside the step kernels and flag handshake between
+    PROCESSES, with the ranks' kernels time-sliced on one device (a kernel that waits for another rank's flag is
+    preempted; generous timeout). So the cross-process halo path is exercised on a single-GPU box too."""
+    return [] if _gpu_count() >= size else ['--shared-gpu']
 
 
-def test_cross_process_karman_on_one_gpu():
-    """tests/test_parallelization_von_karman.py:56-66 of the reference on 2 processes sharing one GPU: every rank's whole
-    local arrays (ghost ring included) must equal what the reference produced on 2 ranks."""
-    out = _torchrun('mp_karman.py', 2, 29570, '--shared-gpu')
-    assert 'OK 2 ranks (one gpu/gloo+ipc)' in out
-
-
-@pytest.mark.multigpu
 @pytest.mark.parametrize('size,depth', [(2, 2), (2, 3), (4, 3), (8, 3)])
-def test_slabs_one_process_per_gpu(size, depth):
-    if _gpu_count() < size:
-        pytest.skip(f'needs {size} GPUs')
-    out = _torchrun('mp_slabs.py', size, 29540 + size, '--depth', str(depth), timeout=300, halo_timeout='10')
-    assert f'OK {size} slabs, one process per GPU, depth {depth}' in out
+def test_slabs_one_process_per_rank(size, depth):
+    """The bench decomposition across processes: slabs with `depth` ghost rows, `depth` steps per pass, edge rows with
+    peer ghost stores + flag handshake on the edge stream, interior on the main stream; calls that end on a pass
+    (FINAL-mode materialisation) and on a one-step launch. Values must equal the single-block C oracle on a field
+    that varies along the slab axis (tests/mp_slabs.py)."""
+    place = _placement(size)
+    out = _torchrun('mp_slabs.py', size, 29540 + size + depth, '--depth', str(depth), *place)
+    assert f'OK {size} slabs, one process per GPU' + (' (shared)' if place else '') + f', depth {depth}' in out
 
 
-@pytest.mark.multigpu
 @pytest.mark.parametrize('size', [2, 4, 8])
-def test_one_process_per_gpu_torchrun(size):
-    if _gpu_count() < size:
-        pytest.skip(f'needs {size} GPUs')
-    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={size}',
-           '--master-addr', '127.0.0.1', '--master-port', str(29500 + size), os.path.join(ROOT, 'tests', 'mp_karman.py')]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT,
-                         env=dict(os.environ, LBM_HALO_TIMEOUT_S='10'))
-    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
-    assert f'OK {size} ranks' in res.stdout
+def test_karman_one_process_per_rank(size):
+    """tests/test_parallelization_von_karman.py:18-66 of the reference across `size` processes on its own get_xy_size
+    grid: every rank's whole local arrays (ghost ring included) must equal what the reference produced on as many
+    ranks, the probe trace and the save_mpiio gather too (tests/mp_karman.py)."""
+    place = _placement(size)
+    out = _torchrun('mp_karman.py', size, 29500 + size, *place)
+    assert f'OK {size} ranks ({"one gpu/gloo+ipc" if place else "gpu/nccl+ipc"})' in out
