@@ -151,10 +151,15 @@ int lbm_set_bc_mode(lbm_ctx *ctx, int mode);
  *   "l2_prefetch"    (2) rows ahead of its march whose source segments the multi-step kernel prefetches into L2 with
  *                    cp.async.bulk.prefetch; 0 = off
  *   "fused_seg"      (0) output rows per thread block of the multi-step kernel; 0 = 8..256 by lattice size
+ *   "cluster"        (1) lattices that fit the distributed shared memory of one thread-block cluster (8 CTAs; up to ~12 000
+ *                    cells, no ghost ring) take ALL steps of a call in one launch of k_cluster_steps: the lattice stays in
+ *                    shared memory, a step ends with a hardware cluster barrier instead of a kernel boundary. 1 = the first
+ *                    four eligible calls are timed alternately on this path and on graph replay and the faster one is kept
+ *                    (same bits either way); 2 = always where the lattice fits; 0 = never
  *   "max_queued_calls" (4) lbm_step call k first waits for call k-4 to finish on the device (bounded host run-ahead:
  *                    a driver loop that never reads a result cannot stop its clock with the GPU far behind); 0 = unbounded
  * Environment overrides at lbm_create: LBM_NO_FUSED=1, LBM_NO_GRAPHS=1, LBM_GENERIC_KERNEL=1, LBM_FUSED_SEG=n,
- * LBM_FUSED_DEPTH=d, LBM_DEEP2=1. */
+ * LBM_FUSED_DEPTH=d, LBM_DEEP2=1, LBM_NO_CLUSTER=1. */
 int lbm_set_option(lbm_ctx *ctx, const char *name, int value);
 /* bytes of device memory the context holds */
 int64_t lbm_device_bytes(const lbm_ctx *ctx);

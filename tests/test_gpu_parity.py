@@ -725,6 +725,62 @@ def test_boundary_rows_everywhere_stay_on_one_step_per_pass(P, oracle):
     lat.close()
 
 
+# ---------------------------------------------------------------------------------------------------------
+# cluster kernel: lattices that fit a thread-block cluster's distributed shared memory take all steps of a call in one launch
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('case', ['periodic_100x50', 'couette_100x100', 'poiseuille_100x50', 'periodic_37x23', 'karman_64x48',
+                                  'periodic_16x1000'])
+def test_cluster_kernel_equals_single_launches_and_the_oracle(P, oracle, case):
+    from lattice_boltzmann_parallel_solver_b200.engine import Lattice
+    BU = P.boundary_utils
+    name, dims = case.split('_')
+    shape = tuple(int(v) for v in dims.split('x'))
+    omega, km, scen = 1.3, None, oracle.c.periodic()
+    if name == 'couette':
+        km, scen = BU.couette_flow_boundary_conditions(*shape, 0.05, 1.0).kind_map(shape), oracle.c.couette(0.05, 1.0)
+    elif name == 'poiseuille':
+        km, scen = BU.poiseuille_flow_boundary_conditions(*shape, 0.3338, 0.3328).kind_map(shape), oracle.c.poiseuille(0.3338, 0.3328)
+    elif name == 'karman':
+        bundle, d = _karman_bundle(P, shape)
+        km, scen = bundle.kind_map(shape), oracle.c.karman(*shape, 1.0, 0.1, d, ghost=0, probe=(shape[0] // 2, 5))
+    f, rho, u = random_state(oracle, shape, 13)
+    px, py = shape[0] // 2, 5
+    clu, one = Lattice(*shape, km), Lattice(*shape, km)
+    clu.set_option('cluster', 2)            # always (the default times it against graph replay first and keeps the faster)
+    one.set_option('cluster', 0)
+    one.set_option('graphs', 0)
+    for lat in (clu, one):
+        lat.probe(px, py, capacity=256)
+        lat.load(f, rho, u, omega)
+    l0 = clu.launches
+    for n in (7, 1, 40, 2, 33):            # odd and even launch lengths, a lone step in between
+        clu.run(n)
+        one.run(n)
+    assert clu.launches - l0 == 5, 'one cluster launch per call (and a one-step launch) expected'
+    for a, b, nm in zip(clu.fields(), one.fields(), 'f rho u'.split()):
+        assert_parity(a, b, f'{case} {nm}')
+    assert_parity(clu.probe_read(1, 83), one.probe_read(1, 83), 'probe ring')
+    ref = oracle.c.run(f, rho, u, omega, scen, 83)
+    for a, b, nm in zip(clu.fields(), ref, 'f rho u'.split()):
+        assert_parity(a, b, f'{case} vs oracle {nm}')
+    clu.run(10, 0.8)                        # omega change: the last step of the previous launch is redone
+    ref = oracle.c.run(*ref, 0.8, scen, 10)
+    for a, b, nm in zip(clu.fields(), ref, 'f rho u'.split()):
+        assert_parity(a, b, f'{case} after omega change {nm}')
+    # default policy: the first four long calls alternate between the cluster kernel and graph replay (timed), then one
+    # of them is kept; whatever is chosen, the bits are the same
+    auto = Lattice(*shape, km)
+    auto.load(f, rho, u, omega)
+    for _ in range(7):
+        auto.run(64)
+    ref = oracle.c.run(f, rho, u, omega, scen, 7 * 64)
+    for a, b, nm in zip(auto.fields(), ref, 'f rho u'.split()):
+        assert_parity(a, b, f'{case} auto-tuned path {nm}')
+    auto.close()
+    clu.close()
+    one.close()
+
+
 def test_options_and_state_errors(P, oracle):
     from lattice_boltzmann_parallel_solver_b200 import _native as N
     from lattice_boltzmann_parallel_solver_b200.engine import Lattice
