@@ -438,9 +438,18 @@ def main():
         ny = size
         nx_local = size // world if strong else size
         prof = EPS * np.sin(np.divide(2 * np.pi * np.arange(ny), ny))   # initial_values.py:83-88
-        if workload == 'karman':
-            assert world == 1, 'the BC-bearing workload is a single-GPU measurement'
+        if workload == 'karman' and world == 1:
             lat = karman_lattice(nx_local, ny, bc_mode)
+        elif workload == 'karman':
+            # N GPUs: the rule set on the GLOBAL (nx_local * N) x ny lattice, slabs with two ghost rows that carry the
+            # neighbour's kinds; two steps per pass on every rank (fluid two-step kernel + strip windows next to boundary
+            # rows and slab edges), every rank ends a call with a one-step launch (option "tail": same launch sequence)
+            g = 2
+            km = karman_slab_kind_map(nx_local * world, ny, rank * nx_local - g, nx_local + 2 * g)
+            lat = Lattice(nx_local + 2 * g, ny, km, ghost=(g, 0), bc_mode=bc_mode)
+            lat.set_option('tail', 1)
+            cart = ldist.comm_world().Create_cart(dims=[world, 1], periods=[True, True])
+            par.communication(cart).attach(lat)
         elif world == 1:
             lat = Lattice(nx_local, ny)
         else:
@@ -589,11 +598,12 @@ def main():
         strong_rec = sub_record('shear', True, 32768, ssteps, max(3, min(args.warmup, 12)))
         strong_rec['scaling'] = 'strong'
         strong_rec['workload'] = f'strong scaling: 32768x32768 total periodic shear-wave lattice over {world} GPU(s) (BASELINE.json configs[4])'
-        if world == 1:
-            karman_rec = sub_record('karman', False, args.size, max(8, min(args.steps, 60)), max(3, min(args.warmup, 12)))
-            karman_rec['workload'] = (f'von Karman rule set (inlet row, outlet rows, plate of ny/4.5 at nx/4; nu 0.04, u_in 0.1) on '
-                                      f'{args.size}x{args.size}: the BC-bearing case of SURVEY.md section 8(d)')
-            karman_rec['vs_periodic'] = karman_rec['value'] / mlups if 'value' in karman_rec else None
+        karman_rec = sub_record('karman', False, args.size, max(8, min(args.steps, 60)), max(3, min(args.warmup, 12)))
+        karman_rec['scaling'] = 'weak'
+        karman_rec['workload'] = (f'von Karman rule set (inlet row, outlet rows, plate of ny/4.5 at nx/4; nu 0.04, u_in 0.1) on the '
+                                  f'global {args.size * world}x{args.size} lattice ({args.size}x{args.size} per GPU), two steps per '
+                                  f'pass: the BC-bearing case of SURVEY.md section 8(d)')
+        karman_rec['vs_periodic'] = karman_rec['value'] / mlups if 'value' in karman_rec else None
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:   # CPU baseline: rank 0 at N=1 only
@@ -688,6 +698,45 @@ def karman_lattice(nx, ny, bc_mode):
     bundle = BU.BoundaryBundle('von_karman_serial', (nx, ny))
     bundle.add(B.inlet((nx, ny), 1.0, 0.1)).add(B.outlet()).add(B.rigid_object(plate))
     return Lattice(nx, ny, bundle.kind_map((nx, ny)), bc_mode=bc_mode)
+
+
+def karman_slab_kind_map(nx_global, ny, row0, nrows):
+    """Rows [row0, row0 + nrows) (periodic in the global row index) of the kind map `karman_lattice` builds for an
+    nx_global x ny lattice, WITHOUT building the global arrays (131072 x 16384 at 8 GPUs): the rule set touches five
+    global rows only — inlet on row 0, outlet on rows nx-2 / nx-1, the plate on rows nx//4 and nx//4 + 1 — and is
+    written here row by row with the same emitters' effect, in the same order (inlet, outlet, plate). Tested against
+    the global construction at small sizes (tests/test_host_logic.py). Ghost rows of a slab carry the neighbour's kinds."""
+    from lattice_boltzmann_parallel_solver_b200 import _native as N
+    from lattice_boltzmann_parallel_solver_b200 import boundary_conditions as B
+    from lattice_boltzmann_parallel_solver_b200 import boundary_spec as S
+    km = S.KindMap((nrows, ny))
+    d = int(ny / 4.5) // 2 * 2
+    y_lo, y_hi = ny // 2 - d // 2, ny // 2 + d // 2 - 1          # plate cells y_lo .. y_hi (the two ends are corners)
+    x0 = nx_global // 4
+    inlet_values = B.inlet((1, 1), 1.0, 0.1).values
+    outlet_rule = S.rule(N.RULE_OUTLET)
+    rows = [(i, (row0 + i) % nx_global) for i in range(nrows)]
+    for i, X in rows:                                            # inlet (boundary_conditions.py:250-251)
+        if X == 0:
+            km.constant((i, slice(None)), inlet_values)
+    for i, X in rows:                                            # outlet (:279-280)
+        if X == nx_global - 1:
+            km.flag((i, slice(None)), rules_for={3: outlet_rule, 6: outlet_rule, 7: outlet_rule})
+        if X == nx_global - 2:
+            km.flag((i, slice(None)), bits=N.CELL_OUTLET_SRC)
+    for i, X in rows:                                            # plate (:133-163): full cells, then the four corners
+        if X == x0:
+            km.bounce((i, slice(y_lo + 1, y_hi)), [1, 5, 8])
+        if X == x0 + 1:
+            km.bounce((i, slice(y_lo + 1, y_hi)), [3, 6, 7])
+    for i, X in rows:
+        if X == x0:
+            km.bounce((i, y_hi), [1, 8])
+            km.bounce((i, y_lo), [1, 5])
+        if X == x0 + 1:
+            km.bounce((i, y_hi), [3, 7])
+            km.bounce((i, y_lo), [3, 6])
+    return km
 
 
 def run_e2e(args, lat, world, rank, nx_local, ny, prof, barrier):

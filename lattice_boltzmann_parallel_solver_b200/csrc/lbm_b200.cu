@@ -105,6 +105,7 @@ struct StepParams {
     // ghost snapshot (see snapshot_ghosts): [2][9][pitch] for rows 0 / NX-1, [2][9][NX] for columns 0 / NY-1
     double *snap_row, *snap_col;
     int use_snap;              // FINAL launches: read ghost cells from the snapshot instead of S
+    int no_snap;               // launches through a strip window: take no ghost snapshot (the source is not S)
     // fix-up list
     const int2 *cells;
     int n_cells;
@@ -412,7 +413,7 @@ __device__ __forceinline__ void finish_cell(const StepParams &P, int x, int y, c
     if (flags & (LBM_CELL_PBC_IN_SRC | LBM_CELL_PBC_OUT_SRC)) store_pbc(P, flags, y, s, p, e);
     if (HALO) {
         store_halo(P, x, y, s);
-        snapshot_ghosts(P, x, y);
+        if (!P.no_snap) snapshot_ghosts(P, x, y);
     }
 }
 
@@ -760,6 +761,9 @@ __global__ void __launch_bounds__(T, 4) k_step2x(const __grid_constant__ StepPar
 #ifndef LBM_MERGE_LEVELS
 #define LBM_MERGE_LEVELS 1   // levels 2..D of an iteration in one basic block (instruction-level parallelism over 2(D-1) cells)
 #endif
+#ifndef LBM_RING_ALL9
+#define LBM_RING_ALL9 0   // the unshifted populations (0, 1, 3) travel through the rings too instead of held registers
+#endif
 #ifndef LBM_LATE_LOAD
 #define LBM_LATE_LOAD 1
 #endif
@@ -770,7 +774,7 @@ template <int T, int D>
 struct Deep {
     static constexpr int W = 2 * T - 4 * (D - 1);   // output columns per block
     static constexpr int RS = 2 * T;                // doubles per ring row
-    static constexpr int SP = 18;                   // slot-populations per ring
+    static constexpr int SP = LBM_RING_ALL9 ? 27 : 18;   // slot-populations per ring
     static constexpr int MINB = D == 2 ? 3 : (D == 3 ? LBM_D3_MINB : 2);
     static constexpr int SMEM = (D - 1) * SP * RS * (int)sizeof(double);
 };
@@ -784,6 +788,7 @@ __global__ void __launch_bounds__(T, Deep<T, D>::MINB) k_stepNx(const __grid_con
     constexpr int W = Deep<T, D>::W, RS = Deep<T, D>::RS, SP = Deep<T, D>::SP;
     constexpr bool MERGE = LBM_MERGE_LEVELS != 0;
     constexpr bool LATE_LOAD = LBM_LATE_LOAD != 0 && D >= 3;
+    constexpr bool ALL9 = LBM_RING_ALL9 != 0;
     const int tid = threadIdx.x;
     const int y0 = (blockIdx.x + P.strip0) * W;
     int x0, x1;
@@ -853,6 +858,12 @@ __global__ void __launch_bounds__(T, Deep<T, D>::MINB) k_stepNx(const __grid_con
         R[(10 + q4) * RS] = sa[8];  R[(10 + q4) * RS + T] = sb[8];
         R[(14 + q2) * RS] = sa[6];  R[(14 + q2) * RS + T] = sb[6];
         R[(16 + q2) * RS] = sa[7];  R[(16 + q2) * RS + T] = sb[7];
+        if (ALL9) {   // own pair only, never shifted: one 128-bit word per population (3: 2 slots, 0: 3 slots, 1: 4 slots)
+            double2 *O = reinterpret_cast<double2 *>(ring + (size_t)b * SP * RS) + tid;
+            O[(18 + q2) * T] = make_double2(sa[3], sb[3]);
+            O[(20 + q3) * T] = make_double2(sa[0], sb[0]);
+            O[(23 + q4) * T] = make_double2(sa[1], sb[1]);
+        }
     };
     // the six y-moving pulls of the pair on intermediate row q: 5, 8 from row q-1; 2, 4 from row q; 6, 7 from row q+1.
     // Even cell (column 2t): c_y = +1 pulls the odd column of pair t-1, c_y = -1 the odd column of pair t;
@@ -866,6 +877,13 @@ __global__ void __launch_bounds__(T, Deep<T, D>::MINB) k_stepNx(const __grid_con
         ha[8] = R[(10 + a4) * RS + T + tid]; hb[8] = R[(10 + a4) * RS + tp];
         ha[6] = R[(14 + d2) * RS + T + tm];  hb[6] = R[(14 + d2) * RS + tid];
         ha[7] = R[(16 + d2) * RS + T + tid]; hb[7] = R[(16 + d2) * RS + tp];
+        if (ALL9) {   // 3 from row q+1, 0 from row q, 1 from row q-1
+            const double2 *O = reinterpret_cast<const double2 *>(R) + tid;
+            const double2 v3 = O[(18 + d2) * T], v0 = O[(20 + m3) * T], v1 = O[(23 + a4) * T];
+            ha[3] = v3.x; hb[3] = v3.y;
+            ha[0] = v0.x; hb[0] = v0.y;
+            ha[1] = v1.x; hb[1] = v1.y;
+        }
     };
 
     // unshifted populations in flight between the levels (a = even column, b = odd column of the pair):
@@ -906,6 +924,7 @@ __global__ void __launch_bounds__(T, Deep<T, D>::MINB) k_stepNx(const __grid_con
         bool slow = false, sl_a[D + 1] = {}, sl_b[D + 1] = {};
         auto gather_level = [&](int d, double (&ha)[9], double (&hb)[9]) {
             ring_gather(d - 2, q - (unsigned)(2 * d - 3), ha, hb);
+            if (ALL9) return;
             if (d == 2) {
                 ha[0] = g0a;    hb[0] = g0b;
                 ha[1] = g1a[1]; hb[1] = g1b[1];
@@ -964,7 +983,7 @@ __global__ void __launch_bounds__(T, Deep<T, D>::MINB) k_stepNx(const __grid_con
                     }
                 }
             }
-            if (d < D) {   // hand the unshifted populations of the row just written to level d+1
+            if (!ALL9 && d < D) {   // hand the unshifted populations of the row just written to level d+1
                 k1a[d - 1][2] = k1a[d - 1][1]; k1a[d - 1][1] = k1a[d - 1][0]; k1a[d - 1][0] = ta[d][1];
                 k1b[d - 1][2] = k1b[d - 1][1]; k1b[d - 1][1] = k1b[d - 1][0]; k1b[d - 1][0] = tb[d][1];
                 k0a[d - 1][1] = k0a[d - 1][0]; k0a[d - 1][0] = ta[d][0];
@@ -1006,8 +1025,10 @@ __global__ void __launch_bounds__(T, Deep<T, D>::MINB) k_stepNx(const __grid_con
 #pragma unroll
             for (int d = D; d >= 2; d--) store_level(d);
         }
-        g1a[1] = g1a[0]; g1a[0] = sa[1]; g0a = sa[0];
-        g1b[1] = g1b[0]; g1b[0] = sb[1]; g0b = sb[0];
+        if (!ALL9) {
+            g1a[1] = g1a[0]; g1a[0] = sa[1]; g0a = sa[0];
+            g1b[1] = g1b[0]; g1b[0] = sb[1]; g0b = sb[0];
+        }
     }
     if (HALO) halo_signal(P);
 }
@@ -1555,6 +1576,8 @@ struct lbm_ctx {
     int fused_depth = 3;          // time steps per pass of the multi-step kernel, 2..4 (LBM_FUSED_DEPTH / option "fused_depth")
     bool deep2 = false;           // depth-2 passes through k_stepNx<2> (18-slot ring) instead of k_step2x (option "deep2")
     bool fused_exact = false;     // tests: an even lbm_step(n) is exactly n/2 two-step passes (no one-step tail)
+    bool force_tail = false;      // end every call with a one-step launch even on fluid lattices (option "tail": ranks of one
+                                  // decomposition must take the same launch sequence, and those with boundary cells need the tail)
     int last_depth = 0;           // S[cur^1] holds S_{t-last_depth}: depth of the pass that produced S_t (0 right after a load)
     // state
     int cur = 0;              // S[cur] = S_t
@@ -1596,7 +1619,7 @@ static deep_fn deep_kernel(int depth, bool halo, bool probe, bool final)
 {
     return depth == 2 ? deep_kernel_d<2>(halo, probe, final) : (depth == 3 ? deep_kernel_d<3>(halo, probe, final) : deep_kernel_d<4>(halo, probe, final));
 }
-static int deep_smem(int depth) { return (depth - 1) * 18 * 2 * kFusedThreads * (int)sizeof(double); }
+static int deep_smem(int depth) { return (depth - 1) * (LBM_RING_ALL9 ? 27 : 18) * 2 * kFusedThreads * (int)sizeof(double); }
 static int deep_width(int depth) { return 2 * kFusedThreads - 4 * (depth - 1); }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -1859,6 +1882,35 @@ extern "C" int lbm_destroy(lbm_ctx *c)
 // one-step mask kernel twice, S_t rows [a-2, b+2) -> window rows [a-1, b+1) of S_{t+1} -> S_{t+2} rows [a, b).
 // For the von Karman rule set (inlet row, plate rows, outlet rows) 13 of the NX rows are strip rows.
 // (pure host logic; lbm_plan_two_step exposes it to the CPU tests)
+// Slabs (gx >= 2 ghost rows per side, no periodic wrap inside the array): the rows this rank computes are [gx, NX-gx);
+// a row is a strip row when a non-fluid cell — on a ghost row too — lies within two rows, and ALWAYS within gx rows of
+// the slab edges: those are the rows that read ghost rows and whose results are stored into the neighbours' ghost rows,
+// which on a lattice with boundary cells is done by the one-step mask kernel (k_step2x knows neither rules nor halos
+// ... the fluid edge launch of two_steps() does, but not next to boundary cells; one code path is enough here).
+static bool plan_rows_slab(int NX, int gx, const std::vector<char> &dirty, std::vector<std::pair<int, int>> &strips,
+                           std::vector<std::pair<int, int>> &clean)
+{
+    strips.clear();
+    clean.clear();
+    const int lo = gx, hi = NX - gx;
+    if (hi - lo < 8 * gx) return false;
+    std::vector<char> strip_row(NX, 0);
+    int n_strip_rows = 0;
+    for (int x = lo; x < hi; x++) {
+        for (int d = -2; d <= 2; d++) strip_row[x] |= dirty[x + d];
+        if (x < lo + gx || x >= hi - gx) strip_row[x] = 1;
+        n_strip_rows += strip_row[x];
+    }
+    if (2 * n_strip_rows > hi - lo) return false;
+    for (int x = lo; x < hi;) {
+        int e = x;
+        while (e < hi && strip_row[e] == strip_row[x]) e++;
+        (strip_row[x] ? strips : clean).push_back({x, e});
+        x = e;
+    }
+    return strips.size() <= 16 && clean.size() <= 16;
+}
+
 static bool plan_rows(int NX, const std::vector<char> &dirty, std::vector<std::pair<int, int>> &strips,
                       std::vector<std::pair<int, int>> &clean)
 {
@@ -1913,12 +1965,10 @@ extern "C" int lbm_plan_two_step(int nx, const uint8_t *row_has_boundary, int *n
     return LBM_OK;
 }
 
-static int plan_strips(lbm_ctx *c, const std::vector<int2> &cells)
+static int plan_strips(lbm_ctx *c, const std::vector<char> &dirty)
 {
-    std::vector<char> dirty(c->NX, 0);
-    for (const int2 &xy : cells) dirty[xy.x] = 1;
     std::vector<std::pair<int, int>> rows, clean;
-    if (!plan_rows(c->NX, dirty, rows, clean)) return LBM_OK;
+    if (!(c->gx ? plan_rows_slab(c->NX, c->gx, dirty, rows, clean) : plan_rows(c->NX, dirty, rows, clean))) return LBM_OK;
     for (const auto &r : rows) {
         lbm_ctx::Strip s = {r.first, r.second, nullptr};
         const size_t bytes = (size_t)9 * (s.b - s.a + 2) * c->pitch * 8;
@@ -2009,7 +2059,8 @@ static int ctx_build(lbm_ctx *c, const lbm_bc_desc *bc)
         c->rho_in = bc->pbc_rho_in;
         c->rho_out = bc->pbc_rho_out;
         std::vector<uint8_t> km((size_t)c->NX * c->pitch, 0);
-        std::vector<int2> cells;
+        std::vector<int2> cells;            // non-fluid cells this rank computes (fix-up list of the edge kernel)
+        std::vector<char> dirty(c->NX, 0);  // rows that hold a non-fluid cell, ghost rows of a slab included
         bool any_pbc = false;
         for (int x = 0; x < c->NX; x++)
             for (int y = 0; y < c->NY; y++) {
@@ -2017,14 +2068,18 @@ static int ctx_build(lbm_ctx *c, const lbm_bc_desc *bc)
                 if (k >= bc->n_kinds) return fail(LBM_ERR_ARG, "bc: kind_map[%d,%d] = %d out of range", x, y, k);
                 km[(size_t)x * c->pitch + y] = k;
                 if (k) {
-                    cells.push_back(make_int2(x, y));
+                    dirty[x] = 1;
+                    // Slabs (ghost_x >= 2): the ghost rows mirror the neighbour's rows and carry THEIR kinds — a multi-step
+                    // pass recomputes the intermediate states of those rows from the ghost values. They are never stored.
+                    const bool slab_ghost = c->gx >= 2 && (x < c->gx || x >= c->NX - c->gx);
+                    if (!slab_ghost) cells.push_back(make_int2(x, y));
                     const lbm_kind &kd = bc->kinds[k];
                     if (kd.flags & (LBM_CELL_PBC_IN_SRC | LBM_CELL_PBC_OUT_SRC)) {
                         any_pbc = true;
                         if ((kd.flags & LBM_CELL_PBC_IN_SRC) && x != c->NX - 2) return fail(LBM_ERR_ARG, "bc: PBC_IN_SRC cells must lie on row nx-2");
                         if ((kd.flags & LBM_CELL_PBC_OUT_SRC) && x != 1) return fail(LBM_ERR_ARG, "bc: PBC_OUT_SRC cells must lie on row 1");
                     }
-                    if (x < c->gx || x >= c->NX - c->gx || (c->gy && (y == 0 || y == c->NY - 1)))
+                    if (!slab_ghost && (x < c->gx || x >= c->NX - c->gx || (c->gy && (y == 0 || y == c->NY - 1))))
                         return fail(LBM_ERR_ARG, "bc: ghost cells must be fluid (the reference applies its closures to the interior view)");
                 }
             }
@@ -2042,9 +2097,12 @@ static int ctx_build(lbm_ctx *c, const lbm_bc_desc *bc)
             CK(cudaMalloc(&c->cells, cells.size() * sizeof(int2)));
             CK(cudaMemcpyAsync(c->cells, cells.data(), cells.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
             // (same size conditions as fused_ok: small lattices never take the two-step pass)
-            if (!any_pbc && !c->gx && !c->gy && c->NY >= 2 * kFusedThreads && (c->NY % 2) == 0 &&
+            if (!any_pbc && c->gx != 1 && !c->gy && c->NY >= 2 * kFusedThreads && (c->NY % 2) == 0 &&
                 (long long)c->NX * c->NY >= kEdgeThreshold)
-                if (int rc = plan_strips(c, cells)) return rc;
+                if (int rc = plan_strips(c, dirty)) return rc;
+        } else if (c->gx >= 2 && std::find(dirty.begin(), dirty.end(), (char)1) != dirty.end() && !any_pbc && !c->gy &&
+                   c->NY >= 2 * kFusedThreads && (c->NY % 2) == 0 && (long long)c->NX * c->NY >= kEdgeThreshold) {
+            if (int rc = plan_strips(c, dirty)) return rc;   // only the neighbours' rows hold boundary cells: still a BC slab
         } else {
             c->has_bc = false;
         }
@@ -2059,8 +2117,8 @@ extern "C" int lbm_create(int device, int nx, int ny, int ghost_x, int ghost_y, 
     *out = nullptr;
     if (nx < 1 || ny < 1) return fail(LBM_ERR_ARG, "lbm_create: lattice must be at least 1x1 (got %dx%d)", nx, ny);
     if (ghost_x < 0 || ghost_x > kMaxDepth || (ghost_y & ~1)) return fail(LBM_ERR_ARG, "lbm_create: ghost_x must be 0..%d and ghost_y 0 or 1", kMaxDepth);
-    if (ghost_x >= 2 && (ghost_y || (bc && bc->kind_map)))
-        return fail(LBM_ERR_ARG, "lbm_create: %d ghost rows (slabs of the multi-step kernel) exist for fluid lattices without y ghosts only", ghost_x);
+    if (ghost_x >= 2 && ghost_y)
+        return fail(LBM_ERR_ARG, "lbm_create: %d ghost rows (slabs of the multi-step kernel) exist for lattices without y ghosts only", ghost_x);
     if ((ghost_x && nx < 4 * ghost_x) || (ghost_y && ny < 3)) return fail(LBM_ERR_ARG, "lbm_create: too few interior cells for the ghost ring");
     lbm_ctx *c = new lbm_ctx;
     c->device = device;
@@ -2114,6 +2172,8 @@ extern "C" int lbm_set_option(lbm_ctx *c, const char *name, int value)
     else if (n == "l2_prefetch") {
         if (value < 0 || value > 8) return fail(LBM_ERR_ARG, "lbm_set_option: l2_prefetch must be 0..8 rows");
         c->l2_prefetch = value;
+    } else if (n == "tail") {
+        c->force_tail = value != 0;
     } else if (n == "cluster") {   // 0 = never, 1 = where measured faster than graph replay (default), 2 = wherever the lattice fits
         if (value < 0 || value > 2) return fail(LBM_ERR_ARG, "lbm_set_option: cluster must be 0, 1 or 2");
         c->use_cluster = value != 0;
@@ -2132,7 +2192,7 @@ extern "C" int lbm_set_option(lbm_ctx *c, const char *name, int value)
         if (value < 2 && value != 0) return fail(LBM_ERR_ARG, "lbm_set_option: fused_seg must be >= 2, or 0 for the default");
         c->fused_seg = value;
     } else
-        return fail(LBM_ERR_ARG, "lbm_set_option: unknown option '%s' (fused, graphs, pdl, generic_kernel, fused_exact, fused_seg, fused_depth, deep2, l2_prefetch, max_queued_calls, cluster)", name);
+        return fail(LBM_ERR_ARG, "lbm_set_option: unknown option '%s' (fused, graphs, pdl, generic_kernel, fused_exact, fused_seg, fused_depth, deep2, l2_prefetch, max_queued_calls, cluster, tail)", name);
     return LBM_OK;
 }
 
@@ -2426,31 +2486,47 @@ static int fused_launch(lbm_ctx *c, StepParams P, int row0a, int na, int row0b, 
 
 // Lattice with boundary cells (plan_strips): k_step2x on the clean rows, two one-step mask launches per strip.
 // All launches read S[src] (and the strip windows) and write disjoint rows of S[dst]: plain stream order.
+// Slabs (gx >= 2): the strips next to the slab edges are the only launches that touch ghost rows. Their first launch
+// (S_t -> window, ghost row gx-1 / NX-gx included) waits for the neighbours' previous pass; their second launch stores
+// the rows within gx of the edge into the neighbours' ghost rows as well, and the last of them publishes the pass.
 static int two_steps_bc(lbm_ctx *c, const StepParams &P0, int src, int dst)
 {
     const int NX = c->NX;
     const bool probe = c->probe && c->px >= 0;
+    const bool slab = c->gx > 0, remote = slab && c->any_remote;
+    const unsigned E = c->halo_epoch;
     for (size_t i = 0; i < c->clean.size(); i += 2) {
         StepParams P = P0;
         const auto ra = c->clean[i], rb = i + 1 < c->clean.size() ? c->clean[i + 1] : std::make_pair(0, 0);
         if (probe && ((c->px >= ra.first && c->px < ra.second) || (c->px >= rb.first && c->px < rb.second))) set_probe(c, P, src, dst);
         if (int rc = fused_launch<false>(c, P, ra.first, ra.second - ra.first, rb.first, rb.second - rb.first, pick_seg(c, c->NX), c->stream)) return rc;
     }
-    for (const auto &s : c->strips) {
+    int last_edge = -1;
+    for (size_t i = 0; i < c->strips.size(); i++)
+        if (slab && (c->strips[i].a == c->gx || c->strips[i].b == NX - c->gx)) last_edge = (int)i;
+    for (size_t i = 0; i < c->strips.size(); i++) {
+        const auto &s = c->strips[i];
+        const bool edge = slab && (s.a == c->gx || s.b == NX - c->gx);
         const int base = (s.a + NX - 1) % NX;
         const long long wplane = (long long)(s.b - s.a + 2) * c->pitch;
         const bool probe_here = probe && ((c->px >= s.a && c->px < s.b) || (c->px + NX >= s.a && c->px + NX < s.b));
         // rows [lo, hi) of the lattice, unwrapped, as (at most) two wrapped ranges
         auto launch_rows = [&](StepParams &P, int lo, int hi) {
-            if (lo < 0) return rows_launch(c, P, lo + NX, -lo, 0, hi, true, false, c->stream);
-            if (hi > NX) return rows_launch(c, P, lo, NX - lo, 0, hi - NX, true, false, c->stream);
-            return rows_launch(c, P, lo, hi - lo, 0, 0, true, false, c->stream);
+            if (lo < 0) return rows_launch(c, P, lo + NX, -lo, 0, hi, true, edge, c->stream);
+            if (hi > NX) return rows_launch(c, P, lo, NX - lo, 0, hi - NX, true, edge, c->stream);
+            return rows_launch(c, P, lo, hi - lo, 0, 0, true, edge, c->stream);
         };
         StepParams P1 = P0;   // S_t -> window: rows a-1 .. b of S_{t+1}
         P1.dst = s.buf;
         P1.dplane = wplane;
         P1.dbase = base;
         P1.out_next = c->outbuf[2];
+        P1.no_snap = 1;
+        if (edge) {           // reads ghost rows: wait for the neighbours; an intermediate state is never stored into theirs
+            fill_halo(c, P1, dst, true);
+            for (int k = 0; k < 9; k++) P1.halo[k].base = nullptr;
+            if (remote) P1.wait_value = E;
+        }
         if (probe_here) set_probe(c, P1, src, 2);
         if (int rc = launch_rows(P1, s.a - 1, s.b + 1)) return rc;
         StepParams P2 = P0;   // window -> S_{t+2} rows a .. b-1
@@ -2458,9 +2534,15 @@ static int two_steps_bc(lbm_ctx *c, const StepParams &P0, int src, int dst)
         P2.plane = wplane;
         P2.sbase = base;
         P2.out_cur = c->outbuf[2];
+        P2.no_snap = 1;
+        if (edge) {
+            fill_halo(c, P2, dst, true);
+            if (remote && (int)i == last_edge) P2.signal_value = E + 1;
+        }
         if (probe_here) set_probe(c, P2, 2, dst);
         if (int rc = launch_rows(P2, s.a, s.b)) return rc;
     }
+    if (remote) c->halo_epoch++;
     return LBM_OK;
 }
 
@@ -2849,7 +2931,7 @@ extern "C" int lbm_step(lbm_ctx *c, double omega, int n_steps)
     // cells end every call with a one-step launch so that the other buffer holds S_{t-1}.
     if (fused_ok(c)) {
         const int D = max_depth(c);
-        const bool no_tail = tail_free(c) || c->fused_exact;
+        const bool no_tail = (tail_free(c) && !c->force_tail) || c->fused_exact;
         while (true) {
             const int d = std::min(D, no_tail ? left : left - 1);
             if (d < 2) break;

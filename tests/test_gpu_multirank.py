@@ -168,3 +168,13 @@ def test_karman_one_process_per_rank(size):
     place = _placement(size)
     out = _torchrun('mp_karman.py', size, 29500 + size, *place)
     assert f'OK {size} ranks ({"one gpu/gloo+ipc" if place else "gpu/nccl+ipc"})' in out
+
+
+@pytest.mark.parametrize('size', [2, 4])
+def test_karman_slabs_two_steps_per_pass_across_ranks(size):
+    """Boundary-bearing lattices on N ranks take two steps per pass too (slabs with two ghost rows that carry the
+    neighbour's kinds; strip windows next to boundary rows and slab edges with ghost stores + flag handshake). With 4
+    ranks the plate sits on the first row of rank 1, i.e. on rank 0's ghost rows. Must equal the single-block oracle."""
+    place = _placement(size)
+    out = _torchrun('mp_karman_slabs.py', size, 29580 + size, *place)
+    assert f'OK {size} karman slabs' in out

@@ -350,3 +350,44 @@ def test_two_step_row_plan_properties():
             assert not near[a:b].any()
         assert (owner == 1).all(), (nx, dirty, plan)
         assert clean == sorted(clean) and strips == sorted(strips)
+
+
+def test_karman_slab_kind_maps_equal_the_global_construction(monkeypatch):
+    """bench.py builds the von Karman rule set of an N-GPU lattice slab by slab (ghost rows included, which carry the
+    neighbour's kinds) without the global arrays; cell by cell it must be the rule set the package's own operators
+    (inlet, outlet, rigid_object — bench.karman_lattice) compile on the global lattice."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from lattice_boltzmann_parallel_solver_b200 import _native as N
+    from lattice_boltzmann_parallel_solver_b200 import boundary_conditions as B
+    from lattice_boltzmann_parallel_solver_b200 import boundary_utils as BU
+    from tests.fake_native import FakeLib
+    fake = FakeLib()
+    monkeypatch.setattr(N, 'load', lambda: fake)
+    monkeypatch.setattr(N, 'device', lambda: 0)
+
+    def effective(km):
+        """per cell: (rule of each population with its K / constant row RESOLVED to values, flags, skip)"""
+        out = {}
+        t = km.table
+        for k, (rules, flags, skip) in enumerate(t.kinds):
+            res = []
+            for i, r in enumerate(rules):
+                typ, row = r & 7, r >> 3
+                val = tuple(t.k_rows[row]) if typ == N.RULE_BOUNCE else (tuple(t.c_rows[row]) if typ == N.RULE_CONST else ())
+                res.append((typ, val))
+            out[k] = (tuple(res), flags, skip)
+        return [[out[int(k)] for k in row] for row in km.map]
+
+    for nxg, ny, world, g in ((64, 36, 4, 2), (96, 45, 3, 2), (40, 20, 2, 3)):
+        d = int(ny / 4.5) // 2 * 2
+        plate = np.zeros((nxg, ny), dtype=bool)
+        plate[nxg // 4, ny // 2 - d // 2:ny // 2 + d // 2] = True
+        bundle = BU.BoundaryBundle('von_karman_serial', (nxg, ny))
+        bundle.add(B.inlet((nxg, ny), 1.0, 0.1)).add(B.outlet()).add(B.rigid_object(plate))
+        want = effective(bundle.kind_map((nxg, ny)))
+        nxl = nxg // world
+        for rank in range(world):
+            got = effective(bench.karman_slab_kind_map(nxg, ny, rank * nxl - g, nxl + 2 * g))
+            for i in range(nxl + 2 * g):
+                assert got[i] == want[(rank * nxl - g + i) % nxg], (nxg, ny, world, rank, i)
