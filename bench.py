@@ -289,13 +289,38 @@ def workload_config(args, world, depth=3):
             'l2': 'populations are 19.3 GB per GPU per buffer >> 126 MB L2; no flush needed'}
 
 
+def bind_to_gpu_numa_node(gpu):
+    """One process per GPU: run (and therefore first-touch its pinned host buffers) on the CPUs NVML reports as local to
+    that GPU, so that eight ranks staging 25.8 GB each do not all pull through one memory controller / inter-socket link.
+    Best effort: returns what was done, never raises."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        pick = cpus & allowed
+        if pick and pick != allowed:
+            os.sched_setaffinity(0, pick)
+            return f'bound to {len(pick)} CPUs local to GPU {gpu}'
+        return f'GPU {gpu}: NVML reports {len(cpus)} local CPUs = the allowed set ({len(allowed)}): nothing to bind'
+    except Exception as e:   # no NVML, restricted container, ...
+        return f'not bound ({type(e).__name__})'
+
+
 def source_sha():
-    """sha256 of the kernel sources: profiles/traffic.json is only quoted for the binary it was captured on."""
+    """sha256 of the hot kernels' source (the marked region of lbm_b200.cu: k_step_pair, k_step2x, k_stepNx, and the
+    arithmetic header): profiles/traffic.json is only quoted for the kernels it was captured on."""
     import hashlib
     h = hashlib.sha256()
-    for name in ('lbm_b200.cu', 'lbm_device.cuh'):
-        with open(os.path.join(ROOT, 'lattice_boltzmann_parallel_solver_b200', 'csrc', name), 'rb') as fh:
-            h.update(fh.read())
+    csrc = os.path.join(ROOT, 'lattice_boltzmann_parallel_solver_b200', 'csrc')
+    with open(os.path.join(csrc, 'lbm_b200.cu'), 'rb') as fh:
+        text = fh.read()
+    a, b = text.find(b'// ==== HOT KERNELS BEGIN'), text.find(b'// ==== HOT KERNELS END')
+    h.update(text[a:b] if 0 <= a < b else text)
+    with open(os.path.join(csrc, 'lbm_device.cuh'), 'rb') as fh:
+        h.update(fh.read())
     return h.hexdigest()
 
 
@@ -408,6 +433,7 @@ def main():
 
     torch.cuda.set_device(local)
     N.set_device(local)
+    affinity = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         ldist.ensure_process_group('nccl')
     assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}'
@@ -635,7 +661,7 @@ def main():
             'metric': 'D2Q9 fp64 MLUPS', 'value': mlups, 'unit': 'MLUPS', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
             'scaling': 'strong' if args.strong else 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': cfg, 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'parity': parity,
+            'config': dict(cfg, cpu_affinity=affinity) if affinity else cfg, 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'parity': parity,
             'roofline': roofline, 'cpu_baseline': cpu, 'strong': strong_rec, 'karman': karman_rec,
             'reference_scaling_test': ref_cfg,
         }

@@ -484,6 +484,8 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepParams
     if (HALO && !FINAL) halo_signal(P);
 }
 
+// ==== HOT KERNELS BEGIN (bench.py hashes this region + lbm_device.cuh: profiles/traffic.json is quoted only for the
+// ==== kernels it was captured on) ====
 // -------------------------------------------------------------------------------------------------------
 // The bandwidth kernel: fluid cells only (no kind byte, no ghost stores), TWO cells per thread along the fast axis.
 //  * blockIdx.y is the row (no integer division), the three row bases are computed once per thread;
@@ -1032,6 +1034,8 @@ __global__ void __launch_bounds__(T, Deep<T, D>::MINB) k_stepNx(const __grid_con
     }
     if (HALO) halo_signal(P);
 }
+
+// ==== HOT KERNELS END ====
 
 // -------------------------------------------------------------------------------------------------------
 // Launch-bound lattices (BASELINE.json configs 1-3: 5 000 - 10 000 cells, 2 500 - 40 000 steps per run): MANY time

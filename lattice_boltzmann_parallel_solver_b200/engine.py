@@ -271,7 +271,15 @@ class Lattice:
 def connect_blocks(blocks, dims):
     """Wire a whole periodic Cartesian topology of lattices that live in THIS process (one per block coordinate,
     possibly on different GPUs): blocks[(cx, cy)] -> Lattice, dims = (x_size, y_size). The multi-process equivalent
-    is `parallelization_utils.communication(comm).attach(lattice)`."""
+    is `parallelization_utils.communication(comm).attach(lattice)`.
+
+    Stepping such blocks: a block's step kernel WAITS (spinning on a flag) until its neighbours have finished the
+    previous step. One process per GPU, that is always safe. Several blocks on ONE device are only safe when a waiting
+    kernel can never keep the kernel it waits for from running: step the blocks with `run_blocks` (which drains every
+    launch group before the next when blocks share a device), or launch them yourself one step at a time with a
+    `sync()` of all blocks in between. Queueing many steps per block asynchronously on a shared device can dead-lock;
+    the wait then times out (LBM_HALO_TIMEOUT_S) and every later call raises LbmTimeoutError — it never returns wrong
+    fields."""
     xs, ys = int(dims[0]), int(dims[1])
     exports = {c: lat.halo_export() for c, lat in blocks.items()}
     for (cx, cy), lat in blocks.items():
@@ -281,6 +289,24 @@ def connect_blocks(blocks, dims):
                     continue
                 lat.halo_connect((dx + 1) * 3 + dy + 1, exports[((cx + dx) % xs, (cy + dy) % ys)])
         lat.halo_finalize()
+
+
+def run_blocks(blocks, n_steps, omega=None, chunk=None):
+    """Advance every lattice of a `connect_blocks` topology by n_steps, safely: all blocks take the same launch groups
+    in lockstep, and when two blocks share a device each group is drained before the next one is queued (see
+    connect_blocks). `chunk` = steps per group (default: 1 on a shared device, all of them otherwise)."""
+    lats = list(blocks.values()) if isinstance(blocks, dict) else list(blocks)
+    shared = len({lat.device for lat in lats}) < len(lats)
+    step = int(chunk) if chunk else (1 if shared else int(n_steps))
+    done = 0
+    while done < n_steps:
+        n = min(step, n_steps - done)
+        for lat in lats:
+            lat.run(n, omega)
+        if shared:
+            for lat in lats:
+                lat.sync()
+        done += n
 
 
 _SHAPES = {'f': lambda nx, ny: (nx, ny, 9), 'rho': lambda nx, ny: (nx, ny), 'u': lambda nx, ny: (nx, ny, 2)}

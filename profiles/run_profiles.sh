@@ -1,25 +1,26 @@
 #!/bin/bash
-# Reproduces the profiles/ evidence on a B200 box:  gpurun --timeout 1500 -- 'bash profiles/run_profiles.sh r01'
+# Reproduces the profiles/ evidence on a B200 box:  gpurun --timeout 1500 -- 'bash profiles/run_profiles.sh r02'
 # (never a bench value: numbers printed under ncu are not reported anywhere)
 set -u
-TAG=${1:-r01}
+TAG=${1:-r02}
 OUT=gpurun_out
 mkdir -p $OUT
-BENCH="python bench.py --steps 7 --warmup 3 --no-e2e --no-cpu --no-ref-config"
+BENCH="python bench.py --steps 9 --warmup 3 --no-e2e --no-cpu --no-ref-config --no-sub --no-parity"
 # 1. launch list of the bench command (cold-cache, serialised: compare SHARES)
-ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches_${TAG}.csv $BENCH > $OUT/launches_${TAG}.log 2>&1
-# 2. full capture of the dominant kernel (two steps per launch) and of the one-step kernel
-ncu --set full --clock-control none --import-source on -k regex:k_step2x -s 1 -c 1 -o $OUT/prof_2x_${TAG} -f $BENCH > $OUT/prof_2x_${TAG}.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_step_pair -s 1 -c 1 -o $OUT/prof_pair_${TAG} -f $BENCH --single-step > $OUT/prof_pair_${TAG}.log 2>&1
-# 2b. BC-bearing workload with two steps per pass: launch list (k_step2x on the clean rows + mask launches on the strips)
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:k_step -s 2 -c 16 --csv \
-    --log-file $OUT/karman_fused_${TAG}.csv $BENCH --workload karman > $OUT/karman_fused_${TAG}.log 2>&1
-[ "${QUICK:-0}" = 1 ] && { ls -la $OUT; exit 0; }
-# 3. BC-bearing workload, one step per pass: flag mask folded into the kernel vs mask-free kernel + edge kernel
-BENCH="$BENCH --single-step"
-for mode in mask edge; do
-  ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed \
-      --clock-control none -k regex:k_step -s 3 -c 6 --csv --log-file $OUT/karman_${mode}_${TAG}.csv \
-      $BENCH --workload karman --bc-mode $mode > $OUT/karman_${mode}_${TAG}.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $OUT/${TAG}_launches.csv $BENCH > $OUT/${TAG}_launches.log 2>&1
+# 2. full captures: the three-step kernel (dominant), the two-step kernel (remainder passes, lattices with boundary cells)
+#    and the one-step kernel
+ncu --set full --clock-control none --import-source on -k regex:k_stepNx -s 1 -c 1 -o $OUT/${TAG}_k_stepNx3 -f $BENCH > $OUT/${TAG}_k_stepNx3.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_step2x -s 1 -c 1 -o $OUT/${TAG}_k_step2x -f $BENCH --depth 2 > $OUT/${TAG}_k_step2x.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_step_pair -s 1 -c 1 -o $OUT/${TAG}_k_step_pair -f $BENCH --single-step > $OUT/${TAG}_k_step_pair.log 2>&1
+for k in k_stepNx3 k_step2x k_step_pair; do
+  ncu -i $OUT/${TAG}_$k.ncu-rep --page raw --csv > $OUT/${TAG}_${k}_full.csv 2>/dev/null
 done
+python tools/make_traffic_json.py $OUT/${TAG}_k_stepNx3_full.csv $OUT/${TAG}_k_step2x_full.csv $OUT/${TAG}_k_step_pair_full.csv > $OUT/traffic.json
+# 3. BC-bearing workload with two steps per pass: launch list (k_step2x on the clean rows + mask launches on the strips)
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:k_step -s 2 -c 16 --csv \
+    --log-file $OUT/${TAG}_karman_fused.csv $BENCH --workload karman > $OUT/${TAG}_karman_fused.log 2>&1
+# 4. the cluster kernel on config 1 (100 x 50, 2000 steps in one launch)
+ncu --set full --clock-control none -k regex:k_cluster -c 1 -o $OUT/${TAG}_k_cluster -f python tools/profile_cluster.py > $OUT/${TAG}_k_cluster.log 2>&1
+ncu -i $OUT/${TAG}_k_cluster.ncu-rep --page raw --csv > $OUT/${TAG}_k_cluster_full.csv 2>/dev/null
 ls -la $OUT

@@ -52,9 +52,8 @@ def test_k_blocks_in_one_process(size):
         lat.load(*init[c], omega)
     for lat in blocks.values():
         lat.sync()
-    for _ in range(11):
-        for lat in blocks.values():
-            lat.run(1)
+    from lattice_boltzmann_parallel_solver_b200.engine import run_blocks
+    run_blocks(blocks, 11)             # lockstep launch groups, drained between groups when blocks share a device
     G = np.zeros((lx, ly, 9))
     for (cx, cy), lat in blocks.items():
         lat.sync()
