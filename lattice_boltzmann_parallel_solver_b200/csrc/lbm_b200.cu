@@ -1607,6 +1607,10 @@ struct lbm_ctx {
 
 static void drop_graphs(lbm_ctx *c);
 static const int kFusedThreads = 128;   // two-steps-per-pass kernel: threads per block
+#ifndef LBM_DEEP_T
+#define LBM_DEEP_T 128
+#endif
+static const int kDeepThreads = LBM_DEEP_T;   // k_stepNx: threads per block (NY >= 2 * max of the two is required)
 static const long long kEdgeThreshold = 1 << 20;   // cells; LBM_BC_AUTO switches to the edge kernel above this
 static const int kMaxDepth = 4;         // deepest multi-step pass (k_stepNx)
 
@@ -1614,7 +1618,7 @@ typedef void (*deep_fn)(const StepParams);
 template <int D>
 static deep_fn deep_kernel_d(bool halo, bool probe, bool final)
 {
-    constexpr int T = kFusedThreads;
+    constexpr int T = kDeepThreads;
     if (final) return k_stepNx<T, D, false, false, true>;
     if (halo) return probe ? k_stepNx<T, D, true, true, false> : k_stepNx<T, D, true, false, false>;
     return probe ? k_stepNx<T, D, false, true, false> : k_stepNx<T, D, false, false, false>;
@@ -1623,8 +1627,8 @@ static deep_fn deep_kernel(int depth, bool halo, bool probe, bool final)
 {
     return depth == 2 ? deep_kernel_d<2>(halo, probe, final) : (depth == 3 ? deep_kernel_d<3>(halo, probe, final) : deep_kernel_d<4>(halo, probe, final));
 }
-static int deep_smem(int depth) { return (depth - 1) * (LBM_RING_ALL9 ? 27 : 18) * 2 * kFusedThreads * (int)sizeof(double); }
-static int deep_width(int depth) { return 2 * kFusedThreads - 4 * (depth - 1); }
+static int deep_smem(int depth) { return (depth - 1) * (LBM_RING_ALL9 ? 27 : 18) * 2 * kDeepThreads * (int)sizeof(double); }
+static int deep_width(int depth) { return 2 * kDeepThreads - 4 * (depth - 1); }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -2101,11 +2105,11 @@ static int ctx_build(lbm_ctx *c, const lbm_bc_desc *bc)
             CK(cudaMalloc(&c->cells, cells.size() * sizeof(int2)));
             CK(cudaMemcpyAsync(c->cells, cells.data(), cells.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
             // (same size conditions as fused_ok: small lattices never take the two-step pass)
-            if (!any_pbc && c->gx != 1 && !c->gy && c->NY >= 2 * kFusedThreads && (c->NY % 2) == 0 &&
+            if (!any_pbc && c->gx != 1 && !c->gy && c->NY >= 2 * std::max(kFusedThreads, kDeepThreads) && (c->NY % 2) == 0 &&
                 (long long)c->NX * c->NY >= kEdgeThreshold)
                 if (int rc = plan_strips(c, dirty)) return rc;
         } else if (c->gx >= 2 && std::find(dirty.begin(), dirty.end(), (char)1) != dirty.end() && !any_pbc && !c->gy &&
-                   c->NY >= 2 * kFusedThreads && (c->NY % 2) == 0 && (long long)c->NX * c->NY >= kEdgeThreshold) {
+                   c->NY >= 2 * std::max(kFusedThreads, kDeepThreads) && (c->NY % 2) == 0 && (long long)c->NX * c->NY >= kEdgeThreshold) {
             if (int rc = plan_strips(c, dirty)) return rc;   // only the neighbours' rows hold boundary cells: still a BC slab
         } else {
             c->has_bc = false;
@@ -2415,7 +2419,7 @@ static int one_step(lbm_ctx *c, int src, double omega, long long t_new)
 
 static bool fused_ok(const lbm_ctx *c)
 {
-    return c->use_fused && (!c->has_bc || c->fused_bc) && !c->gy && c->gx != 1 && c->NY >= 2 * kFusedThreads && (c->NY % 2) == 0 &&
+    return c->use_fused && (!c->has_bc || c->fused_bc) && !c->gy && c->gx != 1 && c->NY >= 2 * std::max(kFusedThreads, kDeepThreads) && (c->NY % 2) == 0 &&
            (c->NX - 2 * c->gx) >= 8 && (long long)c->NX * c->NY >= kEdgeThreshold && (!c->gx || c->halo_ready);
 }
 
@@ -2461,7 +2465,7 @@ static int fused_launch(lbm_ctx *c, StepParams P, int row0a, int na, int row0b, 
         const int W = deep_width(depth);
         dim3 grid((c->NY + W - 1) / W, (na + seg - 1) / seg + (nb + seg - 1) / seg);
         P.n_blocks = (int)(grid.x * grid.y);
-        deep_kernel(depth, HALO, P.probe != nullptr, false)<<<grid, T, deep_smem(depth), st>>>(P);
+        deep_kernel(depth, HALO, P.probe != nullptr, false)<<<grid, kDeepThreads, deep_smem(depth), st>>>(P);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "%d-step kernel launch failed: %s", depth, cudaGetErrorString(e));
         c->launches++;
@@ -2706,7 +2710,10 @@ static void cluster_plan(lbm_ctx *c)
         const long long per = (long long)R * c->NY;
         const size_t smem = (size_t)2 * 9 * per * sizeof(double);
         if (per > 2048 || smem > 220 * 1024) continue;
-        const int m = per > 512 ? 2 : 1;     // blocks of <= 512 threads keep the whole cell update in registers (128 per thread)
+        // one cell per thread up to 768 threads (more warps hide the latency of the cell update better than the larger
+        // register budget of a smaller block does: 1.56 vs 1.70 us per step on config 1), two cells per thread above
+        const int mlim = getenv("LBM_CLUSTER_MLIM") ? atoi(getenv("LBM_CLUSTER_MLIM")) : 768;   // (A/B knob)
+        const int m = per > mlim ? 2 : 1;
         const int threads = (int)std::min<long long>(1024, ((per + m - 1) / m + 31) / 32 * 32);
         cluster_fn fn = cluster_kernel(mask, m, threads);
         if (cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -3001,7 +3008,7 @@ static int materialize_rows(lbm_ctx *c, int x0, int x1, int y0, int y1, double *
             P.pf = 0;
             P.strip0 = y0 / W;
             dim3 grid((y1 + W - 1) / W - P.strip0, (nr + P.seg - 1) / P.seg);
-            deep_kernel(d, false, false, true)<<<grid, kFusedThreads, deep_smem(d), c->stream>>>(P);
+            deep_kernel(d, false, false, true)<<<grid, kDeepThreads, deep_smem(d), c->stream>>>(P);
             e = cudaGetLastError();
         } else
             e = c->has_bc ? launch<true, false, true, false>(P, blocks, bs, c->stream) : launch<false, false, true, false>(P, blocks, bs, c->stream);
