@@ -2365,7 +2365,8 @@ static int one_step(lbm_ctx *c, int src, double omega, long long t_new)
     StepParams P;
     fill_common(c, P, src, dst, omega);
     const bool mask = use_mask(c);
-    const bool fix = c->has_bc && !mask;   // mask-free kernel + thin fix-up kernel over the non-fluid cells
+    // mask-free kernel + thin fix-up kernel over the non-fluid cells (none on a slab whose only boundary cells sit on its ghost rows)
+    const bool fix = c->has_bc && !mask && c->n_cells > 0;
     const bool halo = c->halo_ready;
     const bool remote = halo && c->any_remote;
     fill_halo(c, P, dst, true);
