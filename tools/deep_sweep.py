@@ -46,7 +46,7 @@ if '--d23' in sys.argv:
 for name, depth, deep2 in configs:
     lat.set_option('fused_depth', depth)
     lat.set_option('deep2', deep2)
-    for seg in ((128,) if quick else (32, 64, 128, 256)):
+    for seg in ((128,) if quick else (32, 64, 128, 256, 0)):       # 0 = the library's choice (wave-aware)
         lat.set_option('fused_seg', seg)
         for pf in (PFS if PFS else ((2,) if quick else (0, 2, 4))):
             lat.set_option('l2_prefetch', pf)

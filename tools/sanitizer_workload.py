@@ -14,17 +14,32 @@ from oracle import lbm_numpy as onp, lbm_c as oc
 shape = (1024, 1024)
 rng = np.random.default_rng(0)
 rho = rng.uniform(0.9, 1.1, shape); u = rng.uniform(-0.05, 0.05, shape + (2,)); f = onp.equilibrium(rho, u)
-lat = Lattice(*shape); lat.probe(100, 1022, 16); lat.load(f, rho, u, 1.2); lat.run(5)
-ref = oc.run(f, rho, u, 1.2, oc.periodic(), 5)
-print('fused ok', all(np.array_equal(a, b) for a, b in zip(lat.fields(), ref)))
+for depth, steps in ((3, 7), (3, 6), (2, 5), (4, 8)):    # k_stepNx<3> (+ one-step launch / ending on a pass: FINAL re-run), k_step2x, k_stepNx<4>
+    lat = Lattice(*shape); lat.set_option('fused_depth', depth); lat.set_option('fused_seg', 32)
+    lat.probe(100, 1022, 16); lat.load(f, rho, u, 1.2); lat.run(steps)
+    ref = oc.run(f, rho, u, 1.2, oc.periodic(), steps)
+    print(f'{depth} steps per pass, {steps} steps ok', all(np.array_equal(a, b) for a, b in zip(lat.fields(), ref)),
+          np.array_equal(lat.fields(region=(500, 503, 250, 259))[2], ref[2][500:503, 250:259]))
+    lat.close()
+lat = Lattice(*shape); lat.set_option('deep2', 1); lat.set_option('fused_depth', 2); lat.load(f, rho, u, 1.2); lat.run(4)
+print('k_stepNx<2> ok', all(np.array_equal(a, b) for a, b in zip(lat.fields(), oc.run(f, rho, u, 1.2, oc.periodic(), 4))))
 lat.close()
 n = 2052
-blk = {(0, 0): Lattice(n + 4, 512, ghost=(2, 0))}
-connect_blocks(blk, (1, 1))
-blk[(0, 0)].load_equilibrium(1.0, ux_y=0.01 * np.sin(np.arange(512) / 7.0)); blk[(0, 0)].run(5); blk[(0, 0)].sync()
-print('two-row slab (self neighbour) ran')
-blk[(0, 0)].close()
+for g in (2, 3):                                          # slabs with self neighbour: edge launches with ghost stores
+    blk = {(0, 0): Lattice(n + 2 * g, 512, ghost=(g, 0))}
+    connect_blocks(blk, (1, 1))
+    blk[(0, 0)].load_equilibrium(1.0, ux_y=0.01 * np.sin(np.arange(512) / 7.0)); blk[(0, 0)].run(7); blk[(0, 0)].sync()
+    print(f'{g}-row slab (self neighbour) ran, interior rows materialised', blk[(0, 0)].fields(region=(g, g + 4, 0, 512))[1].shape)
+    blk[(0, 0)].close()
+# cluster kernel: periodic, Couette (two cells per thread), Poiseuille (pressure-periodic stores into other CTAs' shared memory)
 import lattice_boltzmann_parallel_solver_b200 as P
+for name, shp, mk, scen, om in (('periodic', (100, 50), None, oc.periodic(), 1.1),
+                                ('couette', (100, 100), lambda s: P.boundary_utils.couette_flow_boundary_conditions(*s, 0.05, 1.0).kind_map(s), oc.couette(0.05, 1.0), 1.0),
+                                ('poiseuille', (100, 50), lambda s: P.boundary_utils.poiseuille_flow_boundary_conditions(*s, 0.3338, 0.3328).kind_map(s), oc.poiseuille(0.3338, 0.3328), 1.5)):
+    r4 = rng.uniform(0.9, 1.1, shp); u4 = rng.uniform(-0.05, 0.05, shp + (2,)); f4 = onp.equilibrium(r4, u4)
+    l4 = Lattice(*shp, mk(shp) if mk else None); l4.set_option('cluster', 2); l4.probe(7, 5, 64); l4.load(f4, r4, u4, om); k0 = l4.launches; l4.run(33)
+    print('cluster', name, l4.launches - k0 == 1, all(np.array_equal(a, b) for a, b in zip(l4.fields(), oc.run(f4, r4, u4, om, scen, 33))))
+    l4.close()
 from lattice_boltzmann_parallel_solver_b200 import _native as N
 # two steps per pass on a lattice WITH boundary cells: k_step2x on the clean rows, mask launches through strip windows
 shape = (4096, 256)
