@@ -1036,173 +1036,6 @@ __global__ void __launch_bounds__(T, Deep<T, D>::MINB) k_stepNx(const __grid_con
     if (HALO) halo_signal(P);
 }
 
-// -------------------------------------------------------------------------------------------------------
-// Three steps per pass, WARP-SPECIALISED: the same column strips, row segments and rings as k_stepNx<T,3>, but the three
-// levels run in three warp groups of one block (T threads each, 3T per block) that are coupled only through the rings:
-// group g produces rows of S_{t+g+1}; full / done mbarriers per ring row let a producer run up to two rows ahead of its
-// consumer, no block-wide barrier. A thread carries the state of ONE level (one pair of cells in flight, <= 80
-// registers), so 2 blocks = 24 warps share an SM (k_stepNx: 8 warps with four cells in flight each): thread-level
-// instead of instruction-level parallelism for the latency of the fp64 chains. Price: ALL nine populations cross the
-// rings (the unshifted ones as one 128-bit word per pair): 27 slot-populations = 54 KB per ring.
-// Row p of a ring (p counts the producer's rows) may be overwritten when the consumer has finished row p-3 — the same
-// condition for all three population classes, which is what the 4 / 3 / 2 slot counts encode.
-// -------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
-{
-    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-    unsigned done;
-    do {
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
-    } while (!done);
-}
-
-template <int T>
-__global__ void __launch_bounds__(3 * T, 2) k_step3ws(const __grid_constant__ StepParams P)
-{
-    extern __shared__ double ring[];   // [2 rings][27 slot-populations][2T] then 16 mbarriers
-    constexpr int D = 3, W = 2 * T - 4 * (D - 1), RS = 2 * T, SP = 27;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(ring + 2 * SP * RS);   // full[ring][4], done[ring][4]
-    const int grp = threadIdx.x / T, tid = threadIdx.x - grp * T;
-    if (threadIdx.x < 16) mbar_init(bars + threadIdx.x, T);
-    __syncthreads();
-    const int y0 = (blockIdx.x + P.strip0) * W;
-    int x0, x1;
-    {
-        const int rb = blockIdx.y;
-        const int nsa = (P.na + P.seg - 1) / P.seg;
-        if (rb < nsa) {
-            x0 = P.row0a + rb * P.seg;
-            x1 = min(x0 + P.seg, P.row0a + P.na);
-        } else {
-            x0 = P.row0b + (rb - nsa) * P.seg;
-            x1 = min(x0 + P.seg, P.row0b + P.nb);
-        }
-    }
-    const int yo = y0 - 2 * (D - 1) + 2 * tid;
-    const int ca = yo < 0 ? yo + P.NY : (yo >= P.NY ? yo - P.NY : yo);
-    const long long pl = P.plane;
-    auto wrapx = [&](int r) { return r < 0 ? r + P.NX : (r >= P.NX ? r - P.NX : r); };
-    const int tm = tid > 0 ? tid - 1 : 0, tp = tid < T - 1 ? tid + 1 : T - 1;
-    auto ring_store = [&](int b, unsigned q, const double (&sa)[9], const double (&sb)[9]) {
-        double *R = ring + (size_t)b * SP * RS + tid;
-        const unsigned q3 = q % 3u, q4 = q & 3u, q2 = q & 1u;
-        R[(0 + q3) * RS] = sa[2];   R[(0 + q3) * RS + T] = sb[2];
-        R[(3 + q3) * RS] = sa[4];   R[(3 + q3) * RS + T] = sb[4];
-        R[(6 + q4) * RS] = sa[5];   R[(6 + q4) * RS + T] = sb[5];
-        R[(10 + q4) * RS] = sa[8];  R[(10 + q4) * RS + T] = sb[8];
-        R[(14 + q2) * RS] = sa[6];  R[(14 + q2) * RS + T] = sb[6];
-        R[(16 + q2) * RS] = sa[7];  R[(16 + q2) * RS + T] = sb[7];
-        double2 *O = reinterpret_cast<double2 *>(ring + (size_t)b * SP * RS) + tid;
-        O[(18 + q2) * T] = make_double2(sa[3], sb[3]);
-        O[(20 + q3) * T] = make_double2(sa[0], sb[0]);
-        O[(23 + q4) * T] = make_double2(sa[1], sb[1]);
-    };
-    auto ring_gather = [&](int b, unsigned q, double (&ha)[9], double (&hb)[9]) {
-        const double *R = ring + (size_t)b * SP * RS;
-        const unsigned m3 = q % 3u, a4 = (q - 1u) & 3u, d2 = (q + 1u) & 1u;
-        ha[2] = R[(0 + m3) * RS + T + tm];   hb[2] = R[(0 + m3) * RS + tid];
-        ha[4] = R[(3 + m3) * RS + T + tid];  hb[4] = R[(3 + m3) * RS + tp];
-        ha[5] = R[(6 + a4) * RS + T + tm];   hb[5] = R[(6 + a4) * RS + tid];
-        ha[8] = R[(10 + a4) * RS + T + tid]; hb[8] = R[(10 + a4) * RS + tp];
-        ha[6] = R[(14 + d2) * RS + T + tm];  hb[6] = R[(14 + d2) * RS + tid];
-        ha[7] = R[(16 + d2) * RS + T + tid]; hb[7] = R[(16 + d2) * RS + tp];
-        const double2 *O = reinterpret_cast<const double2 *>(R) + tid;
-        const double2 v3 = O[(18 + d2) * T], v0 = O[(20 + m3) * T], v1 = O[(23 + a4) * T];
-        ha[3] = v3.x; hb[3] = v3.y;
-        ha[0] = v0.x; hb[0] = v0.y;
-        ha[1] = v1.x; hb[1] = v1.y;
-    };
-    auto relax_pair = [&](const double (&fa)[9], const double (&fb)[9], double omega, double (&sa)[9], double (&sb)[9]) {
-        double uax, uay, ubx, uby;
-        bool slow_a = false, slow_b = false;
-        relax_fast(fa, omega, sa, uax, uay, slow_a);
-        relax_fast(fb, omega, sb, ubx, uby, slow_b);
-        if (slow_a | slow_b) {
-            if (slow_a) relax_redo(fa, omega, sa, uax, uay);
-            if (slow_b) relax_redo(fb, omega, sb, ubx, uby);
-        }
-    };
-    uint64_t *full0 = bars, *done0 = bars + 4, *full1 = bars + 8, *done1 = bars + 12;
-    // ring rows are counted from the producer's first row: ring 0 from x0-2, ring 1 from x0-1
-    if (grp == 0) {
-        const int cm = ca == 0 ? P.NY - 1 : ca - 1, cq = ca + 2 >= P.NY ? ca + 2 - P.NY : ca + 2;
-        const int n = x1 - x0 + 4;
-        for (int p = 0; p < n; p++) {
-            const int j = x0 - 2 + p;
-            if (tid == 0 && P.pf && p + P.pf < n) {   // L2 prefetch of the nine source segments of row j + pf
-                const int jj = j + P.pf, c0 = max(y0 - 2 * D, 0);
-                const unsigned bytes = (unsigned)(min(y0 - 2 * (D - 1) + 2 * T + 2, P.pitch) - c0) * 8u;
-                const double *r0 = P.src + (long long)wrapx(jj) * P.pitch + c0, *rm = P.src + (long long)wrapx(jj - 1) * P.pitch + c0,
-                             *rp = P.src + (long long)wrapx(jj + 1) * P.pitch + c0;
-                constexpr int cx[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1};
-#pragma unroll
-                for (int i = 0; i < 9; i++)
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((cx[i] == 1 ? rm : (cx[i] == -1 ? rp : r0)) + i * pl), "r"(bytes)
-                                 : "memory");
-            }
-            double fa[9], fb[9], sa[9], sb[9];
-            {
-                const double *r0 = P.src + (long long)wrapx(j) * P.pitch, *rm = P.src + (long long)wrapx(j - 1) * P.pitch,
-                             *rp = P.src + (long long)wrapx(j + 1) * P.pitch;
-                const double2 v0 = ld2(r0 + ca), v1 = ld2(rm + pl + ca), v3 = ld2(rp + 3 * pl + ca);
-                fa[0] = v0.x; fb[0] = v0.y;
-                fa[1] = v1.x; fb[1] = v1.y;
-                fa[3] = v3.x; fb[3] = v3.y;
-                fa[2] = ldS(r0 + 2 * pl + cm); fb[2] = ldS(r0 + 2 * pl + ca);
-                fa[5] = ldS(rm + 5 * pl + cm); fb[5] = ldS(rm + 5 * pl + ca);
-                fa[6] = ldS(rp + 6 * pl + cm); fb[6] = ldS(rp + 6 * pl + ca);
-                fa[4] = ldS(r0 + 4 * pl + ca + 1); fb[4] = ldS(r0 + 4 * pl + cq);
-                fa[7] = ldS(rp + 7 * pl + ca + 1); fb[7] = ldS(rp + 7 * pl + cq);
-                fa[8] = ldS(rm + 8 * pl + ca + 1); fb[8] = ldS(rm + 8 * pl + cq);
-            }
-            relax_pair(fa, fb, P.omega, sa, sb);
-            if (p >= 4) mbar_wait(done0 + ((p - 3) & 3), ((p - 3) >> 2) & 1);
-            ring_store(0, (unsigned)p + 16u, sa, sb);
-            mbar_arrive(full0 + (p & 3));
-        }
-    } else if (grp == 1) {
-        const int n = x1 - x0 + 2;          // rows x0-1 .. x1: ring-0 index p = 1 + i, ring-1 index i
-        mbar_arrive(done0 + 0);             // (ring row 0 is never a consumer row: keeps the phase count of slot 0 in step)
-        for (int i = 0; i < n; i++) {
-            const int p = i + 1;
-            double ha[9], hb[9], ta[9], tb[9];
-            mbar_wait(full0 + ((p + 1) & 3), ((p + 1) >> 2) & 1);
-            ring_gather(0, (unsigned)p + 16u, ha, hb);
-            mbar_arrive(done0 + (p & 3));
-            relax_pair(ha, hb, P.omega, ta, tb);
-            if (i >= 4) mbar_wait(done1 + ((i - 3) & 3), ((i - 3) >> 2) & 1);
-            ring_store(1, (unsigned)i + 16u, ta, tb);
-            mbar_arrive(full1 + (i & 3));
-        }
-    } else {
-        const int n = x1 - x0;              // rows x0 .. x1-1: ring-1 index i = 1 + k
-        const bool out_pair = tid >= D - 1 && tid <= T - D && yo < P.NY;
-        mbar_arrive(done1 + 0);
-        for (int k = 0; k < n; k++) {
-            const int i = k + 1;
-            double ha[9], hb[9], ta[9], tb[9];
-            mbar_wait(full1 + ((i + 1) & 3), ((i + 1) >> 2) & 1);
-            ring_gather(1, (unsigned)i + 16u, ha, hb);
-            mbar_arrive(done1 + (i & 3));
-            relax_pair(ha, hb, P.omega_last, ta, tb);
-            if (out_pair) {
-                double *o = P.dst + (long long)wrapx(x0 + k) * P.pitch + yo;
-#pragma unroll
-                for (int q = 0; q < 9; q++) st2(o + q * pl, ta[q], tb[q]);
-            }
-        }
-    }
-}
-
 // ==== HOT KERNELS END ====
 
 // -------------------------------------------------------------------------------------------------------
@@ -1748,7 +1581,6 @@ struct lbm_ctx {
     int n_sm = 148;               // multiprocessors of the device (wave-aware segment length)
     bool wave_seg = true;         // option "wave_seg": pick the segment length whose block count fills whole waves
     int fused_depth = 3;          // time steps per pass of the multi-step kernel, 2..4 (LBM_FUSED_DEPTH / option "fused_depth")
-    bool ws = false;              // three-step passes through the warp-specialised k_step3ws (option "ws", LBM_WS=1)
     bool deep2 = false;           // depth-2 passes through k_stepNx<2> (18-slot ring) instead of k_step2x (option "deep2")
     bool fused_exact = false;     // tests: an even lbm_step(n) is exactly n/2 two-step passes (no one-step tail)
     bool force_tail = false;      // end every call with a one-step launch even on fluid lattices (option "tail": ranks of one
@@ -1799,7 +1631,6 @@ static deep_fn deep_kernel(int depth, bool halo, bool probe, bool final)
     return depth == 2 ? deep_kernel_d<2>(halo, probe, final) : (depth == 3 ? deep_kernel_d<3>(halo, probe, final) : deep_kernel_d<4>(halo, probe, final));
 }
 static int deep_smem(int depth) { return (depth - 1) * (LBM_RING_ALL9 ? 27 : 18) * 2 * kDeepThreads * (int)sizeof(double); }
-static int ws_smem() { return 2 * 27 * 2 * 128 * (int)sizeof(double) + 16 * 8; }
 static int deep_width(int depth) { return 2 * kDeepThreads - 4 * (depth - 1); }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -2181,7 +2012,6 @@ static int ctx_build(lbm_ctx *c, const lbm_bc_desc *bc)
         CK(cudaFuncSetAttribute(k_step2x<kFusedThreads, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         CK(cudaFuncSetAttribute(k_step2x<kFusedThreads, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         CK(cudaFuncSetAttribute(k_step2x<kFusedThreads, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CK(cudaFuncSetAttribute(k_step3ws<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_smem()));
         for (int d = 2; d <= kMaxDepth; d++)
             for (int v = 0; v < 5; v++)
                 CK(cudaFuncSetAttribute((const void *)deep_kernel(d, v & 1, (v >> 1) & 1, v == 4), cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -2317,7 +2147,6 @@ extern "C" int lbm_create(int device, int nx, int ny, int ghost_x, int ghost_y, 
     if (const char *g = getenv("LBM_FUSED_SEG")) c->fused_seg = atoi(g) >= 2 ? atoi(g) : 0;
     if (const char *g = getenv("LBM_FUSED_DEPTH")) c->fused_depth = std::min(kMaxDepth, std::max(2, atoi(g)));
     if (const char *g = getenv("LBM_DEEP2")) c->deep2 = atoi(g) != 0;
-    if (const char *g = getenv("LBM_WS")) c->ws = atoi(g) != 0;
     if (const char *t = getenv("LBM_HALO_TIMEOUT_S")) c->timeout_cycles = (long long)(atof(t) * 2e9);
     if (int rc = ctx_build(c, bc)) {
         std::string keep = g_err;
@@ -2373,13 +2202,12 @@ extern "C" int lbm_set_option(lbm_ctx *c, const char *name, int value)
         c->fused_depth = value;
     } else if (n == "deep2") {
         c->deep2 = value != 0;
-    } else if (n == "ws") {
-        c->ws = value != 0;
+
     } else if (n == "fused_seg") {
         if (value < 2 && value != 0) return fail(LBM_ERR_ARG, "lbm_set_option: fused_seg must be >= 2, or 0 for the default");
         c->fused_seg = value;
     } else
-        return fail(LBM_ERR_ARG, "lbm_set_option: unknown option '%s' (fused, graphs, pdl, generic_kernel, fused_exact, fused_seg, fused_depth, deep2, ws, l2_prefetch, max_queued_calls, cluster, tail, wave_seg)", name);
+        return fail(LBM_ERR_ARG, "lbm_set_option: unknown option '%s' (fused, graphs, pdl, generic_kernel, fused_exact, fused_seg, fused_depth, deep2, l2_prefetch, max_queued_calls, cluster, tail, wave_seg)", name);
     return LBM_OK;
 }
 
@@ -2662,9 +2490,6 @@ static int fused_launch(lbm_ctx *c, StepParams P, int row0a, int na, int row0b, 
         const int W = deep_width(depth);
         dim3 grid((c->NY + W - 1) / W, (na + seg - 1) / seg + (nb + seg - 1) / seg);
         P.n_blocks = (int)(grid.x * grid.y);
-        if (depth == 3 && c->ws && !HALO && !P.probe && kDeepThreads == 128)
-            k_step3ws<128><<<grid, 3 * 128, ws_smem(), st>>>(P);
-        else
         deep_kernel(depth, HALO, P.probe != nullptr, false)<<<grid, kDeepThreads, deep_smem(depth), st>>>(P);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "%d-step kernel launch failed: %s", depth, cudaGetErrorString(e));
