@@ -469,11 +469,10 @@ def main():
         elif workload == 'karman':
             # N GPUs: the rule set on the GLOBAL (nx_local * N) x ny lattice, slabs with two ghost rows that carry the
             # neighbour's kinds; two steps per pass on every rank (fluid two-step kernel + strip windows next to boundary
-            # rows and slab edges), every rank ends a call with a one-step launch (option "tail": same launch sequence)
+            # rows and slab edges)
             g = 2
             km = karman_slab_kind_map(nx_local * world, ny, rank * nx_local - g, nx_local + 2 * g)
             lat = Lattice(nx_local + 2 * g, ny, km, ghost=(g, 0), bc_mode=bc_mode)
-            lat.set_option('tail', 1)
             cart = ldist.comm_world().Create_cart(dims=[world, 1], periods=[True, True])
             par.communication(cart).attach(lat)
         elif world == 1:

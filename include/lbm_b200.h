@@ -143,14 +143,16 @@ int lbm_set_bc_mode(lbm_ctx *ctx, int mode);
  *   "pdl"            (1) programmatic dependent launch between the step kernels of launch-bound lattices: the next step's
  *                    blocks are launched and read their parameters / kind bytes while the current step still runs
  *   "generic_kernel" (0) force the one-cell-per-thread step kernel
- *   "fused_exact"    (0) lattices WITH boundary cells normally end every call with a one-step launch, so that the other
- *                    buffer holds S_{t-1} for materialisation; 1 = no such tail (results cannot be materialised until one
- *                    more single step is taken). Fluid lattices never need the tail: after a call that ended on a
- *                    d-step pass, results are materialised by re-running that pass with its last level writing
- *                    f_post / rho / u instead of colliding, and a changed omega redoes the pass's last collision.
+ *   "tail"           (0) 1 = every call ends with a one-step launch, so that the other buffer holds S_{t-1} (round 1's
+ *                    behaviour; A/B and tests). By default a call may END on a multi-step pass: results are then
+ *                    materialised by re-running that pass with its last level writing f_post / rho / u instead of
+ *                    colliding (fluid rows) or from the strip windows, which keep S_{t-1} of the boundary rows; a changed
+ *                    omega redoes the pass's last collision.
+ *   "fused_exact"    (0) with "tail" = 1: no tail after all (tests)
+ *   "wave_seg"       (1) among the long segments pick the one whose block count fills whole waves of resident blocks
  *   "l2_prefetch"    (2) rows ahead of its march whose source segments the multi-step kernel prefetches into L2 with
  *                    cp.async.bulk.prefetch; 0 = off
- *   "fused_seg"      (0) output rows per thread block of the multi-step kernel; 0 = 8..256 by lattice size
+ *   "fused_seg"      (0) output rows per thread block of the multi-step kernel; 0 = 8..512 by lattice size
  *   "cluster"        (1) lattices that fit the distributed shared memory of one thread-block cluster (8 CTAs; up to ~12 000
  *                    cells, no ghost ring) take ALL steps of a call in one launch of k_cluster_steps: the lattice stays in
  *                    shared memory, a step ends with a hardware cluster barrier instead of a kernel boundary. 1 = the first

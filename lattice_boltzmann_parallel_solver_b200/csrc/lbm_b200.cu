@@ -2431,10 +2431,10 @@ static bool fused_ok(const lbm_ctx *c)
            (c->NX - 2 * c->gx) >= 8 && (long long)c->NX * c->NY >= kEdgeThreshold && (!c->gx || c->halo_ready);
 }
 
-// May a call END on a multi-step pass? Yes where results of time t can be rebuilt from S_{t-d} by re-running the pass
-// with its last level in FINAL mode: fluid lattices (slabs expose their own rows only). Lattices with boundary cells
-// (strip windows) end every call with a one-step launch instead, unless option fused_exact says otherwise.
-static bool tail_free(const lbm_ctx *c) { return !c->has_bc; }
+// May a call END on a multi-step pass? Yes: results of time t are rebuilt from S_{t-d} by re-running the pass with its
+// last level in FINAL mode (fluid rows), or from the strip windows, which keep S_{t-1} of the boundary rows (lattices
+// with boundary cells); option "tail" = 1 still ends every call with a one-step launch (A/B, tests).
+static bool tail_free(const lbm_ctx *) { return true; }
 
 // Deepest pass this lattice can take: lattices with boundary cells stay on two steps (strip windows), slabs cannot look
 // further than their ghost rows.
@@ -2476,11 +2476,12 @@ static int pick_seg(const lbm_ctx *c, int rows, int depth = 2)
 }
 
 template <bool HALO>
-static int fused_launch(lbm_ctx *c, StepParams P, int row0a, int na, int row0b, int nb, int seg, cudaStream_t st, int depth = 2)
+static int fused_launch(lbm_ctx *c, StepParams P, int row0a, int na, int row0b, int nb, int seg, cudaStream_t st, int depth = 2,
+                        bool force_deep = false)
 {
     if (na + nb <= 0) return LBM_OK;
     constexpr int T = kFusedThreads;
-    if (depth > 2 || c->deep2) {   // k_stepNx
+    if (depth > 2 || c->deep2 || force_deep) {   // k_stepNx
         P.row0a = row0a;
         P.na = na;
         P.row0b = row0b;
@@ -2532,7 +2533,9 @@ static int two_steps_bc(lbm_ctx *c, const StepParams &P0, int src, int dst)
         StepParams P = P0;
         const auto ra = c->clean[i], rb = i + 1 < c->clean.size() ? c->clean[i + 1] : std::make_pair(0, 0);
         if (probe && ((c->px >= ra.first && c->px < ra.second) || (c->px >= rb.first && c->px < rb.second))) set_probe(c, P, src, dst);
-        if (int rc = fused_launch<false>(c, P, ra.first, ra.second - ra.first, rb.first, rb.second - rb.first, pick_seg(c, c->NX), c->stream)) return rc;
+        // (a redo with a new omega for the last collision needs the kernel that knows omega_last: k_stepNx<2>)
+        if (int rc = fused_launch<false>(c, P, ra.first, ra.second - ra.first, rb.first, rb.second - rb.first, pick_seg(c, c->NX), c->stream, 2,
+                                         P0.omega_last != P0.omega)) return rc;
     }
     int last_edge = -1;
     for (size_t i = 0; i < c->strips.size(); i++)
@@ -2567,6 +2570,7 @@ static int two_steps_bc(lbm_ctx *c, const StepParams &P0, int src, int dst)
         P2.plane = wplane;
         P2.sbase = base;
         P2.out_cur = c->outbuf[2];
+        P2.omega = P0.omega_last;
         P2.no_snap = 1;
         if (edge) {
             fill_halo(c, P2, dst, true);
@@ -2588,7 +2592,7 @@ static int two_steps(lbm_ctx *c, int src, double omega, int depth = 2, double om
     if (c->has_bc) return two_steps_bc(c, P, src, dst);
     set_probe(c, P, src, dst);
     const int g = c->gx, xlo = g, xhi = c->NX - g;
-    if (!g) return fused_launch<false>(c, P, xlo, xhi - xlo, 0, 0, pick_seg(c, xhi - xlo, depth), c->stream, depth);
+    if (!g) return fused_launch<false>(c, P, xlo, xhi - xlo, 0, 0, pick_seg(c, xhi - xlo, depth), c->stream, depth, P.omega_last != P.omega);
     // two-row slabs: the 2 + 2 edge rows (readers of the ghost rows, writers of the neighbours') first on the
     // high-priority stream with the flag handshake, the interior overlaps with their NVLink stores
     const bool remote = c->any_remote;
@@ -2601,11 +2605,12 @@ static int two_steps(lbm_ctx *c, int src, double omega, int depth = 2, double om
         Pe.wait_value = E;
         Pe.signal_value = E + 1;
     }
-    if (int rc = fused_launch<true>(c, Pe, xlo, g, xhi - g, g, g, c->stream_edge, depth)) return rc;
+    if (int rc = fused_launch<true>(c, Pe, xlo, g, xhi - g, g, g, c->stream_edge, depth, P.omega_last != P.omega)) return rc;
     CK(cudaEventRecord(c->ev_edge, c->stream_edge));
     StepParams Pi = P;
     for (int s = 0; s < 9; s++) Pi.halo[s].base = nullptr;
-    if (int rc = fused_launch<false>(c, Pi, xlo + g, xhi - xlo - 2 * g, 0, 0, pick_seg(c, xhi - xlo - 2 * g, depth), c->stream, depth)) return rc;
+    if (int rc = fused_launch<false>(c, Pi, xlo + g, xhi - xlo - 2 * g, 0, 0, pick_seg(c, xhi - xlo - 2 * g, depth), c->stream, depth,
+                                     P.omega_last != P.omega)) return rc;
     CK(cudaStreamWaitEvent(c->stream, c->ev_edge, 0));
     if (remote) c->halo_epoch++;
     return LBM_OK;
@@ -2902,7 +2907,7 @@ extern "C" int lbm_step(lbm_ctx *c, double omega, int n_steps)
     if (omega != c->omega) {
         // S[cur] was collided with the previous call's omega. Redo that collision from the retained S_{t-d}: the last
         // launch again (a one-step launch, or a multi-step pass whose LAST level collides with the new omega).
-        if (c->t == 0 || c->last_depth < 1 || (c->last_depth > 1 && c->has_bc))
+        if (c->t == 0 || c->last_depth < 1)
             return fail(LBM_ERR_STATE, "omega differs from the one the resident state was collided with and the previous state is not retained: upload again");
         if (c->any_remote) return fail(LBM_ERR_STATE, "changing omega between steps is not supported with remote halo neighbours: upload again");
         if (c->last_depth == 1) {
@@ -3021,20 +3026,56 @@ static int materialize_rows(lbm_ctx *c, int x0, int x1, int y0, int y1, double *
         P.o_rho = rho || !to_host ? c->stage_rho : nullptr;
         P.o_u = u || !to_host ? c->stage_u : nullptr;
         const int blocks = nr * P.bpr;
-        cudaError_t e;
-        if (c->last_depth > 1) {
-            // the call ended on a multi-step pass: S[cur^1] is S_{t-d}. Re-run the pass over these rows with its last level
-            // in FINAL mode (f_post / rho / u of time t instead of the collision), column strips that meet [y0, y1) only
-            const int d = c->last_depth, W = deep_width(d);
-            P.use_snap = 0;
-            P.row0b = 0;
-            P.nb = 0;
-            P.seg = std::min(nr, 64);
-            P.pf = 0;
-            P.strip0 = y0 / W;
-            dim3 grid((y1 + W - 1) / W - P.strip0, (nr + P.seg - 1) / P.seg);
-            deep_kernel(d, false, false, true)<<<grid, kDeepThreads, deep_smem(d), c->stream>>>(P);
-            e = cudaGetLastError();
+        cudaError_t e = cudaSuccess;
+        // the call ended on a multi-step pass: S[cur^1] is S_{t-d}. Re-run the pass over rows [lo, lo + n) with its last
+        // level in FINAL mode (f_post / rho / u of time t instead of the collision), column strips that meet [y0, y1) only
+        auto deep_final = [&](StepParams Q, int lo, int n, int d) {
+            const int W = deep_width(d);
+            Q.use_snap = 0;
+            Q.row0a = lo;
+            Q.na = n;
+            Q.row0b = 0;
+            Q.nb = 0;
+            Q.seg = std::min(n, 64);
+            Q.pf = 0;
+            Q.strip0 = y0 / W;
+            dim3 grid((y1 + W - 1) / W - Q.strip0, (n + Q.seg - 1) / Q.seg);
+            deep_kernel(d, false, false, true)<<<grid, kDeepThreads, deep_smem(d), c->stream>>>(Q);
+            c->launches++;
+            return cudaGetLastError();
+        };
+        if (c->last_depth > 1 && c->has_bc) {
+            // lattice with boundary cells after a two-step pass: clean rows as above; strip rows from their WINDOW, which still
+            // holds S_{t-1} of the strip (+ one row each side) from the pass's first launch — one FINAL mask launch
+            auto owner = [&](int x) -> const lbm_ctx::Strip * {   // the strip that holds lattice row x (strips may wrap), or null
+                for (const auto &st : c->strips)
+                    if ((x >= st.a && x < st.b) || (x + c->NX >= st.a && x + c->NX < st.b)) return &st;
+                return nullptr;
+            };
+            for (int lo = xa; lo < xa + nr && e == cudaSuccess;) {
+                const lbm_ctx::Strip *in_strip = owner(lo);
+                int hi = lo + 1;
+                while (hi < xa + nr && owner(hi) == in_strip) hi++;
+                if (in_strip) {
+                    StepParams Q = P;
+                    Q.src = in_strip->buf;
+                    Q.plane = (long long)(in_strip->b - in_strip->a + 2) * c->pitch;
+                    Q.sbase = (in_strip->a + c->NX - 1) % c->NX;
+                    Q.out_cur = c->outbuf[2];
+                    Q.use_snap = 0;
+                    Q.row0a = lo;
+                    Q.na = hi - lo;
+                    e = launch<true, false, true, false>(Q, (hi - lo) * P.bpr, bs, c->stream);
+                    c->launches++;
+                } else {
+                    e = deep_final(P, lo, hi - lo, 2);
+                }
+                lo = hi;
+            }
+            c->launches--;   // (counted once more below)
+        } else if (c->last_depth > 1) {
+            e = deep_final(P, xa, nr, c->last_depth);
+            c->launches--;
         } else
             e = c->has_bc ? launch<true, false, true, false>(P, blocks, bs, c->stream) : launch<false, false, true, false>(P, blocks, bs, c->stream);
         if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "materialize kernel launch failed: %s", cudaGetErrorString(e));
@@ -3060,7 +3101,6 @@ static int check_region(lbm_ctx *c, int x0, int x1, int y0, int y1, const char *
 {
     if (!c) return fail(LBM_ERR_ARG, "%s: null context", who);
     if (!c->loaded || c->t == 0) return fail(LBM_ERR_STATE, "%s: no step taken since the state was loaded — the caller still holds it", who);
-    if (c->last_depth > 1 && c->has_bc) return fail(LBM_ERR_STATE, "%s: the last launch was a multi-step pass on a lattice with boundary cells (fused_exact): take one more step first", who);
     if (x0 < 0 || y0 < 0 || x1 > c->NX || y1 > c->NY || x0 >= x1 || y0 >= y1) return fail(LBM_ERR_ARG, "%s: empty or out-of-range region", who);
     if (c->gx >= 2 && (x0 < c->gx || x1 > c->NX - c->gx)) return fail(LBM_ERR_ARG, "%s: slabs with %d ghost rows expose their interior rows [%d, nx-%d) only", who, c->gx, c->gx, c->gx);
     CK(cudaSetDevice(c->device));

@@ -648,6 +648,10 @@ def test_omega_change_after_a_multi_step_pass(P, oracle):
     ref = oracle.c.run(*ref, 1.6, oracle.c.periodic(), 5)
     for a, b, nm in zip(lat.fields(), ref, 'f rho u'.split()):
         assert_parity(a, b, f'omega change {nm}')
+    lat.run(4, 1.1)                   # the previous call ended on a TWO-step pass (k_step2x): redone by k_stepNx<2>, then 3 + 1
+    ref = oracle.c.run(*ref, 1.1, oracle.c.periodic(), 4)
+    for a, b, nm in zip(lat.fields(), ref, 'f rho u'.split()):
+        assert_parity(a, b, f'omega change after a two-step pass {nm}')
     lat.close()
 
 
@@ -695,15 +699,25 @@ def test_two_steps_per_pass_with_boundary_cells(P, oracle, shape, where, second)
     if second:
         per_pass += 1                    # three clean ranges -> two k_step2x launches
     assert plain.launches - p0 == 2 * 18
-    assert fused.launches - l0 == (3 * per_pass + 2) + 2 + (3 * per_pass + 4) + 4, 'the two-step pass was not used'
+    # 7 = 3 passes + a one-step launch (mask-free kernel + edge list), 1, 8 = 4 passes, 2 = 1 pass: calls may END on a pass
+    # (results are then materialised from the strip windows and by re-running the clean rows in FINAL mode)
+    assert fused.launches - l0 == (3 * per_pass + 2) + 2 + 4 * per_pass + per_pass, 'the two-step pass was not used'
     for a, b, nm in zip(fused.fields(), plain.fields(), 'f rho u'.split()):
         assert_parity(a, b, f'{shape} {where} {nm}')
     assert_parity(fused.probe_read(1, 18), plain.probe_read(1, 18), 'probe ring')
     if not second:
-        ref = oracle.c.run(f, rho, u, 1.41, oracle.c.karman(nx, ny, 1.0, 0.1, d, ghost=0, probe=(px, py)), 18, want_probe=True)
+        scen = oracle.c.karman(nx, ny, 1.0, 0.1, d, ghost=0, probe=(px, py))
+        ref = oracle.c.run(f, rho, u, 1.41, scen, 18, want_probe=True)
         for a, b, nm in zip(fused.fields(), ref, 'f rho u'.split()):
             assert_parity(a, b, f'vs oracle {nm}')
         assert_parity(fused.probe_read(1, 18), ref[3], 'probe vs oracle')
+        sub = fused.fields(region=(nx // 4 - 3, nx // 4 + 4, ny // 2 - 5, ny // 2 + 6))     # a rectangle across strip and clean rows
+        for a, b, nm in zip(sub, ref, 'f rho u'.split()):
+            assert_parity(a, b[nx // 4 - 3:nx // 4 + 4, ny // 2 - 5:ny // 2 + 6], f'region {nm}')
+        fused.run(4, 0.9)           # omega change right after a call that ended on a pass: its last collision is redone
+        ref2 = oracle.c.run(ref[0], ref[1], ref[2], 0.9, scen, 4)
+        for a, b, nm in zip(fused.fields(), ref2, 'f rho u'.split()):
+            assert_parity(a, b, f'after omega change {nm}')
     fused.close()
     plain.close()
 
