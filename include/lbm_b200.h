@@ -149,6 +149,8 @@ int lbm_set_bc_mode(lbm_ctx *ctx, int mode);
  *                    colliding (fluid rows) or from the strip windows, which keep S_{t-1} of the boundary rows; a changed
  *                    omega redoes the pass's last collision.
  *   "fused_exact"    (0) with "tail" = 1: no tail after all (tests)
+ *   "streamed"       (1) lbm_run_host pipelines upload, passes and download over row chunks where it can; 0 = the three calls
+ *   "streamed_chunk_rows" (0) rows per chunk of that pipeline (0 = what fits the 256 MB staging buffers; tests)
  *   "wave_seg"       (1) among the long segments pick the one whose block count fills whole waves of resident blocks
  *   "l2_prefetch"    (2) rows ahead of its march whose source segments the multi-step kernel prefetches into L2 with
  *                    cp.async.bulk.prefetch; 0 = off
@@ -183,6 +185,15 @@ int lbm_init_equilibrium(lbm_ctx *ctx, const double *rho_x, const double *ux_y, 
 int lbm_step(lbm_ctx *ctx, double omega, int n_steps);
 /* Blocks until all queued work of the context is done; reports asynchronous errors. */
 int lbm_sync(lbm_ctx *ctx);
+/* The whole job from and to host memory: lbm_upload(f, rho, u, omega) + lbm_step(omega, n_steps) + lbm_materialize(f_out,
+ * rho_out, u_out) — same results, same final state of the context (the driver loops of src/experiments.py start from host
+ * arrays and look at host arrays when they are done: :121-129, :322-327, :756-767). Output pointers may be NULL or alias
+ * the inputs. On a fluid lattice without ghost rows the three phases are pipelined over row chunks (time-skewed passes:
+ * rows [s_p, X - s_p) of time level p are computable as soon as rows [0, X) have arrived), so that the upload of chunk
+ * c+1, the passes over chunk c and the download of the rows chunk c completed overlap on three streams; other lattices
+ * take the three calls one after the other. Synchronous. */
+int lbm_run_host(lbm_ctx *ctx, const double *f, const double *rho, const double *u, double omega, int n_steps,
+                 double *f_out, double *rho_out, double *u_out);
 /* Number of reference steps taken since the last upload / init. */
 int64_t lbm_time(const lbm_ctx *ctx);
 /* How many kernels this context has launched so far (bench.py's gpu_launches). */

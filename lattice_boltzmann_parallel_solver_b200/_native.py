@@ -80,6 +80,7 @@ SIGNATURES = {
     'lbm_upload': (C.c_int, [_CTX, _DP, _DP, _DP, C.c_double]),
     'lbm_init_equilibrium': (C.c_int, [_CTX, _DP, _DP, C.c_double, C.c_double, C.c_double, C.c_double]),
     'lbm_step': (C.c_int, [_CTX, C.c_double, C.c_int]),
+    'lbm_run_host': (C.c_int, [_CTX, _DP, _DP, _DP, C.c_double, C.c_int, _DP, _DP, _DP]),
     'lbm_sync': (C.c_int, [_CTX]),
     'lbm_time': (C.c_int64, [_CTX]),
     'lbm_launch_count': (C.c_int64, [_CTX]),

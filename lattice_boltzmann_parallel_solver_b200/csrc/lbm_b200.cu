@@ -1562,6 +1562,8 @@ struct lbm_ctx {
     bool use_graphs = true;
     bool pdl = true;              // programmatic dependent launch between the step kernels of launch-bound lattices (option "pdl")
     bool use_fused = true;        // LBM_NO_FUSED=1: one step per pass only (A/B measurements)
+    int streamed_chunk_rows = 0;  // lbm_run_host: rows per chunk (0 = what fits the 256 MB staging buffer; option "streamed_chunk_rows")
+    bool use_streamed = true;     // lbm_run_host pipelines upload / passes / download over row chunks (option "streamed")
     bool use_cluster = true;      // lattices that fit a thread-block cluster's shared memory: many steps per launch (option "cluster")
     int cluster_size = 0;         // 0 = not decided yet, -1 = not possible on this lattice / device, else CTAs per cluster
     int cluster_rows = 0, cluster_threads = 0, cluster_m = 0;
@@ -1598,6 +1600,14 @@ struct lbm_ctx {
     bool halo_ready = false, any_remote = false;
     cudaStream_t stream = nullptr, stream_edge = nullptr;
     cudaEvent_t ev_main = nullptr, ev_edge = nullptr;
+    // lbm_run_host: double-buffered staging (set 0 of the inputs is stage_f / stage_rho / stage_u), copy streams, events
+    struct Streamed {
+        double *in_f[2] = {}, *in_rho[2] = {}, *in_u[2] = {}, *out_f[2] = {}, *out_rho[2] = {}, *out_u[2] = {};
+        cudaStream_t h2d = nullptr, d2h = nullptr;
+        cudaEvent_t in_ready[2] = {}, in_free[2] = {}, out_ready[2] = {}, out_free[2] = {};
+        long long *tclock = nullptr;   // device: time after pass p (probe clock of the skewed schedule)
+        int tclock_cap = 0;
+    } *sr = nullptr;
     // Bounded run-ahead of the host (option "max_queued_calls", default 4): lbm_step call k first waits until call
     // k - max_queued_calls has finished on the device. A driver that never looks at a result inside its loop (the
     // reference's scaling_test stops its clock right after the loop, src/experiments.py:763-769) then cannot run more
@@ -1873,6 +1883,18 @@ extern "C" int lbm_destroy(lbm_ctx *c)
     if (c->probe) cudaFreeHost(c->probe);
     if (c->progress) cudaFreeHost(c->progress);
     if (c->err_host) cudaFreeHost(c->err_host);
+    if (c->sr) {
+        for (int k = 0; k < 2; k++) {
+            if (k) { cudaFree(c->sr->in_f[k]); cudaFree(c->sr->in_rho[k]); cudaFree(c->sr->in_u[k]); }
+            cudaFree(c->sr->out_f[k]); cudaFree(c->sr->out_rho[k]); cudaFree(c->sr->out_u[k]);
+            for (cudaEvent_t e : {c->sr->in_ready[k], c->sr->in_free[k], c->sr->out_ready[k], c->sr->out_free[k]})
+                if (e) cudaEventDestroy(e);
+        }
+        if (c->sr->tclock) cudaFree(c->sr->tclock);
+        if (c->sr->h2d) cudaStreamDestroy(c->sr->h2d);
+        if (c->sr->d2h) cudaStreamDestroy(c->sr->d2h);
+        delete c->sr;
+    }
     for (cudaEvent_t e : c->ev_call)
         if (e) cudaEventDestroy(e);
     for (auto &t : c->tune) {
@@ -2184,6 +2206,11 @@ extern "C" int lbm_set_option(lbm_ctx *c, const char *name, int value)
     else if (n == "l2_prefetch") {
         if (value < 0 || value > 8) return fail(LBM_ERR_ARG, "lbm_set_option: l2_prefetch must be 0..8 rows");
         c->l2_prefetch = value;
+    } else if (n == "streamed") {
+        c->use_streamed = value != 0;
+    } else if (n == "streamed_chunk_rows") {
+        if (value < 0) return fail(LBM_ERR_ARG, "lbm_set_option: streamed_chunk_rows must be >= 0");
+        c->streamed_chunk_rows = value;
     } else if (n == "wave_seg") {
         c->wave_seg = value != 0;
     } else if (n == "tail") {
@@ -2207,7 +2234,7 @@ extern "C" int lbm_set_option(lbm_ctx *c, const char *name, int value)
         if (value < 2 && value != 0) return fail(LBM_ERR_ARG, "lbm_set_option: fused_seg must be >= 2, or 0 for the default");
         c->fused_seg = value;
     } else
-        return fail(LBM_ERR_ARG, "lbm_set_option: unknown option '%s' (fused, graphs, pdl, generic_kernel, fused_exact, fused_seg, fused_depth, deep2, l2_prefetch, max_queued_calls, cluster, tail, wave_seg)", name);
+        return fail(LBM_ERR_ARG, "lbm_set_option: unknown option '%s' (fused, graphs, pdl, generic_kernel, fused_exact, fused_seg, fused_depth, deep2, l2_prefetch, max_queued_calls, cluster, tail, wave_seg, streamed, streamed_chunk_rows)", name);
     return LBM_OK;
 }
 
@@ -3119,6 +3146,201 @@ extern "C" int lbm_materialize(lbm_ctx *c, double *f, double *rho, double *u)
 {
     if (!c) return fail(LBM_ERR_ARG, "lbm_materialize: null context");
     return lbm_materialize_region(c, 0, c->NX, 0, c->NY, f, rho, u);
+}
+
+// ---- whole job from and to host memory, streamed ---------------------------------------------------------------
+// lbm_run_host = lbm_upload + lbm_step(n) + lbm_materialize, same bits, same final state of the context — but on a fluid
+// lattice without ghosts the three phases are PIPELINED over row chunks (time-skewed passes): as soon as rows [0, X) of
+// the initial state are on the device, pass p can be completed on rows [pD, X - pD) (D = steps of a full pass), and
+// rows [PD, X - PD) of the result can already travel back. With 256 MB chunks the host->device
+// copy of chunk c+1, the passes over chunk c (a few hundred microseconds: hidden) and the device->host copy of the
+// rows chunk c completed run concurrently on three streams; the job then takes about max(upload, download) on a
+// full-duplex PCIe link instead of upload + compute + download. Level p lives in S[p % 2]: pass p on rows [a, b)
+// overwrites level p-2 there, which pass p-1 has finished reading because it already completed rows up to b + d_p.
+// The rows within s_p of the periodic seam (x = 0 / NX) are done last, after the last chunk has arrived.
+static int streamed_setup(lbm_ctx *c, int n_levels)
+{
+    if (!c->sr) {
+        c->sr = new lbm_ctx::Streamed;
+        lbm_ctx::Streamed &R = *c->sr;
+        R.in_f[0] = c->stage_f;
+        R.in_rho[0] = c->stage_rho;
+        R.in_u[0] = c->stage_u;
+        CK(cudaMalloc(&R.in_f[1], c->stage_cells * 72));
+        CK(cudaMalloc(&R.in_rho[1], c->stage_cells * 8));
+        CK(cudaMalloc(&R.in_u[1], c->stage_cells * 16));
+        for (int k = 0; k < 2; k++) {
+            CK(cudaMalloc(&R.out_f[k], c->stage_cells * 72));
+            CK(cudaMalloc(&R.out_rho[k], c->stage_cells * 8));
+            CK(cudaMalloc(&R.out_u[k], c->stage_cells * 16));
+            for (cudaEvent_t *e : {&R.in_ready[k], &R.in_free[k], &R.out_ready[k], &R.out_free[k]})
+                CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        }
+        CK(cudaStreamCreateWithFlags(&R.h2d, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&R.d2h, cudaStreamNonBlocking));
+    }
+    if (c->sr->tclock_cap < n_levels) {
+        if (c->sr->tclock) CK(cudaFree(c->sr->tclock));
+        c->sr->tclock = nullptr;
+        CK(cudaMalloc(&c->sr->tclock, (size_t)n_levels * 8));
+        c->sr->tclock_cap = n_levels;
+    }
+    return LBM_OK;
+}
+
+extern "C" int lbm_run_host(lbm_ctx *c, const double *f, const double *rho, const double *u, double omega, int n_steps, double *f_out,
+                            double *rho_out, double *u_out)
+{
+    if (!c || !f || !rho || !u) return fail(LBM_ERR_ARG, "lbm_run_host: null pointer");
+    if (n_steps < 1) return fail(LBM_ERR_ARG, "lbm_run_host: n_steps < 1");
+    const int D = fused_ok(c) ? max_depth(c) : 1;
+    long long chunk_rows = c->stage_cells / c->NY;
+    if (c->streamed_chunk_rows > 0) chunk_rows = std::min<long long>(chunk_rows, c->streamed_chunk_rows);   // (tests)
+    const bool streamed = c->use_streamed && D >= 2 && !c->has_bc && !c->gx && !c->gy && !c->halo_ready && (long long)c->NX >= 2LL * (n_steps + D) + 2 * chunk_rows &&
+                          chunk_rows >= 8;
+    if (!streamed) {   // every other lattice: the three calls
+        if (int rc = lbm_upload(c, f, rho, u, omega)) return rc;
+        if (int rc = lbm_step(c, omega, n_steps)) return rc;
+        if (!f_out && !rho_out && !u_out) return LBM_OK;
+        return lbm_materialize(c, f_out, rho_out, u_out);
+    }
+    // pass plan: the schedule lbm_step would take
+    std::vector<int> depth, s(1, 0);
+    for (int left = n_steps; left > 0;) {
+        const int d = left >= D ? D : left;   // remainder: one two-step pass or one one-step launch
+        depth.push_back(d);
+        s.push_back(s.back() + d);
+        left -= d;
+    }
+    const int NP = (int)depth.size(), NX = c->NX, NY = c->NY;
+    // Row lag of level p behind the upload front: p * D rows, also where a pass is shallower than D. (With the true
+    // s_p a two-step pass after three-step passes would overwrite, in S[p % 2], one row of level p-2 that pass p-1 of
+    // the NEXT chunk still has to read: the lag per pass must cover the deepest read halo.)
+    std::vector<int> lag(NP + 1);
+    for (int p = 0; p <= NP; p++) lag[p] = p * D;
+    const int sP = lag[NP];
+    InitParams Q;
+    if (int rc = begin_load(c, omega, Q)) return rc;
+    if (int rc = streamed_setup(c, NP + 1)) return rc;
+    lbm_ctx::Streamed &R = *c->sr;
+    const bool probe = c->probe && c->px >= 0;
+    {
+        std::vector<long long> tl(s.begin(), s.end());
+        CK(cudaMemcpyAsync(R.tclock, tl.data(), tl.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemsetAsync(c->tcount, 0, 24, c->stream));
+        CK(cudaStreamSynchronize(c->stream));   // (tl is a host temporary)
+        *c->progress = 0;
+    }
+    const bool want_out = f_out || rho_out || u_out;
+    int out_k = 0, n_out = 0;
+
+    // pass p (1-based) over lattice rows [lo, hi) and, optionally, a second range [lo2, hi2)
+    auto run_pass = [&](int p, int lo, int hi, int lo2, int hi2) -> int {
+        if (hi <= lo && hi2 <= lo2) return LBM_OK;
+        if (hi <= lo) { lo = lo2; hi = hi2; lo2 = hi2 = 0; }
+        StepParams P;
+        fill_common(c, P, (p - 1) & 1, p & 1, omega);
+        if (probe) {
+            P.px = c->px;
+            P.py = c->py;
+            P.probe = c->probe;
+            P.progress = c->progress;
+            P.probe_cap = c->probe_cap;
+            P.tc_in = R.tclock + (p - 1);
+            P.tc_out = R.tclock + p;
+        }
+        const int d = depth[p - 1];
+        if (d >= 2) return fused_launch<false>(c, P, lo, hi - lo, lo2, hi2 - lo2, 32, c->stream, d);
+        if (int rc = rows_launch(c, P, lo, hi - lo, 0, 0, false, false, c->stream)) return rc;
+        return hi2 > lo2 ? rows_launch(c, P, lo2, hi2 - lo2, 0, 0, false, false, c->stream) : LBM_OK;
+    };
+    // rows [lo, hi) of the result: the last pass again with its last level in FINAL mode -> staging -> host
+    auto emit_rows = [&](int lo, int hi) -> int {
+        if (!want_out || hi <= lo) return LBM_OK;
+        const int k = out_k;
+        out_k ^= 1;
+        if (n_out >= 2) CK(cudaStreamWaitEvent(c->stream, R.out_free[k], 0));
+        n_out++;
+        StepParams P;
+        fill_common(c, P, (NP - 1) & 1, NP & 1, omega);
+        P.row0a = lo;
+        P.na = hi - lo;
+        P.y0 = 0;
+        P.y1 = NY;
+        P.ox0 = lo;
+        P.oy0 = 0;
+        P.ow = NY;
+        P.o_f = f_out ? R.out_f[k] : nullptr;
+        P.o_rho = rho_out ? R.out_rho[k] : nullptr;
+        P.o_u = u_out ? R.out_u[k] : nullptr;
+        const int d = depth[NP - 1];
+        cudaError_t e;
+        if (d >= 2) {
+            const int W = deep_width(d);
+            P.seg = std::min(hi - lo, 32);
+            P.strip0 = 0;
+            dim3 grid((NY + W - 1) / W, (hi - lo + P.seg - 1) / P.seg);
+            deep_kernel(d, false, false, true)<<<grid, kDeepThreads, deep_smem(d), c->stream>>>(P);
+            e = cudaGetLastError();
+        } else {
+            const int bs = block_size(NY);
+            P.bpr = (NY + bs - 1) / bs;
+            e = launch<false, false, true, false>(P, (hi - lo) * P.bpr, bs, c->stream);
+        }
+        if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "lbm_run_host: materialize launch failed: %s", cudaGetErrorString(e));
+        c->launches++;
+        CK(cudaEventRecord(R.out_ready[k], c->stream));
+        CK(cudaStreamWaitEvent(R.d2h, R.out_ready[k], 0));
+        const size_t n = (size_t)(hi - lo) * NY, o = (size_t)lo * NY;
+        if (f_out) CK(cudaMemcpyAsync(f_out + o * 9, R.out_f[k], n * 72, cudaMemcpyDeviceToHost, R.d2h));
+        if (rho_out) CK(cudaMemcpyAsync(rho_out + o, R.out_rho[k], n * 8, cudaMemcpyDeviceToHost, R.d2h));
+        if (u_out) CK(cudaMemcpyAsync(u_out + o * 2, R.out_u[k], n * 16, cudaMemcpyDeviceToHost, R.d2h));
+        CK(cudaEventRecord(R.out_free[k], R.d2h));
+        return LBM_OK;
+    };
+
+    int chunk = 0;
+    for (int X0 = 0; X0 < NX; X0 += (int)chunk_rows, chunk++) {
+        const int X1 = (int)std::min<long long>(NX, X0 + chunk_rows), k = chunk & 1;
+        const size_t n = (size_t)(X1 - X0) * NY, o = (size_t)X0 * NY;
+        if (chunk >= 2) CK(cudaStreamWaitEvent(R.h2d, R.in_free[k], 0));
+        CK(cudaMemcpyAsync(R.in_f[k], f + o * 9, n * 72, cudaMemcpyHostToDevice, R.h2d));
+        CK(cudaMemcpyAsync(R.in_rho[k], rho + o, n * 8, cudaMemcpyHostToDevice, R.h2d));
+        CK(cudaMemcpyAsync(R.in_u[k], u + o * 2, n * 16, cudaMemcpyHostToDevice, R.h2d));
+        CK(cudaEventRecord(R.in_ready[k], R.h2d));
+        CK(cudaStreamWaitEvent(c->stream, R.in_ready[k], 0));
+        Q.in_f = R.in_f[k];
+        Q.in_rho = R.in_rho[k];
+        Q.in_u = R.in_u[k];
+        if (int rc = first_collide(c, Q, X0, X1 - X0)) return rc;
+        CK(cudaEventRecord(R.in_free[k], c->stream));
+        // level p is now computable on rows [s_p, X1 - s_p); new with this chunk: from X0 - s_p on
+        for (int p = 1; p <= NP; p++)
+            if (int rc = run_pass(p, std::max(X0 - lag[p], lag[p]), X1 - lag[p], 0, 0)) return rc;
+        if (int rc = emit_rows(std::max(X0 - sP, sP), X1 - sP)) return rc;
+    }
+    // the periodic seam: rows [NX - lag_p, NX) and [0, lag_p) of level p, in pass order; then their results
+    for (int p = 1; p <= NP; p++)
+        if (int rc = run_pass(p, NX - lag[p], NX, 0, lag[p])) return rc;
+    if (int rc = emit_rows(NX - sP, NX)) return rc;
+    if (int rc = emit_rows(0, sP)) return rc;
+    // the context is now where lbm_upload + lbm_step(n_steps) would have left it
+    c->cur = NP & 1;
+    c->t = n_steps;
+    c->last_depth = depth[NP - 1];
+    c->omega = omega;
+    c->loaded = true;
+    {
+        long long tt[3] = {0, 0, 0};
+        tt[c->cur] = n_steps;
+        tt[c->cur ^ 1] = n_steps - depth[NP - 1];
+        tt[2] = n_steps;
+        CK(cudaMemcpyAsync(c->tcount, tt, 24, cudaMemcpyHostToDevice, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaStreamSynchronize(R.d2h));
+    CK(cudaStreamSynchronize(R.h2d));
+    return async_error(c, "lbm_run_host");
 }
 
 extern "C" int lbm_minmax(lbm_ctx *c, int x0, int x1, int y0, int y1, double out[4])

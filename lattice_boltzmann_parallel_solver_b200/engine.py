@@ -134,6 +134,26 @@ class Lattice:
         self.omega = omega
         self.time += int(n_steps)
 
+    def run_host(self, f, rho, u, omega, n_steps, out=None):
+        """The whole job from and to host arrays: load(f, rho, u, omega) + run(n_steps) + fields(), same results — on a
+        fluid lattice without ghosts upload, time steps and download are pipelined over row chunks (lbm_run_host).
+        `out` = (f_out, density_out, velocity_out) arrays to fill (any may be None; they may be the inputs themselves);
+        default: fresh arrays. Returns the three output arrays."""
+        f = N.as_f64(f, (self.nx, self.ny, 9), 'f')
+        rho = N.as_f64(rho, (self.nx, self.ny), 'density')
+        u = N.as_f64(u, (self.nx, self.ny, 2), 'velocity')
+        assert 0 < omega < 2 and n_steps >= 1
+        if out is None:
+            out = (np.empty_like(f), np.empty_like(rho), np.empty_like(u))
+        for a, shape in zip(out, ((self.nx, self.ny, 9), (self.nx, self.ny), (self.nx, self.ny, 2))):
+            assert a is None or (a.shape == shape and a.dtype == np.float64 and a.flags.c_contiguous)
+        N.check(self.lib.lbm_run_host(self._ctx, N.dptr(f), N.dptr(rho), N.dptr(u), float(omega), int(n_steps),
+                                      N.dptr(out[0]), N.dptr(out[1]), N.dptr(out[2])))
+        self.omega, self.time = float(omega), int(n_steps)
+        self._probe_t0, self._watch = 0, None
+        self._generation += 1
+        return out
+
     def sync(self):
         N.check(self.lib.lbm_sync(self._ctx))
 

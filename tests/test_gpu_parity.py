@@ -795,6 +795,50 @@ def test_cluster_kernel_equals_single_launches_and_the_oracle(P, oracle, case):
     one.close()
 
 
+# ---------------------------------------------------------------------------------------------------------
+# the whole job from and to host memory, pipelined over row chunks (lbm_run_host)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('steps,chunk,depth', [(20, 160, 3), (7, 96, 3), (6, 64, 3), (5, 200, 2), (13, 48, 4), (1, 64, 3)])
+def test_streamed_run_from_and_to_host_memory(P, oracle, steps, chunk, depth):
+    """Upload, time-skewed passes and download overlap chunk by chunk; results, probe samples and the state the context is
+    left in must be those of load + run + fields — against the C oracle on a random field, for every remainder of the pass
+    plan (ends on a three-step / two-step pass or a one-step launch) and with outputs aliasing the inputs."""
+    from lattice_boltzmann_parallel_solver_b200.engine import Lattice
+    shape = (4096, 512)
+    f, rho, u = random_state(oracle, shape, 100 + steps)
+    lat = Lattice(*shape)
+    lat.set_option('fused_depth', depth)
+    lat.set_option('streamed_chunk_rows', chunk)
+    px, py = 3, 77                       # a probe row inside the periodic seam
+    lat.probe(px, py, capacity=64)
+    l0 = lat.launches
+    fo, ro, uo = f.copy(), rho.copy(), u.copy()
+    out = lat.run_host(fo, ro, uo, 1.23, steps, out=(fo, ro, uo))        # in place
+    assert lat.launches - l0 > 4096 // chunk, 'the streamed schedule was not taken'
+    ref = oracle.c.run(f, rho, u, 1.23, oracle.c.periodic(), steps)
+    for a, b, nm in zip(out, ref, 'f rho u'.split()):
+        assert_parity(a, b, f'streamed {steps} steps {nm}')
+    plain = Lattice(*shape)
+    plain.set_option('fused', 0)
+    plain.probe(px, py, capacity=64)
+    plain.load(f, rho, u, 1.23)
+    plain.run(steps)
+    assert_parity(lat.probe_read(1, steps), plain.probe_read(1, steps), 'probe ring')
+    for a, b, nm in zip(lat.fields(), ref, 'f rho u'.split()):          # the context holds the state of time `steps` ...
+        assert_parity(a, b, f'state after the streamed run {nm}')
+    lat.run(4, 0.9)                                                      # ... and goes on from it (with a new omega)
+    plain.run(4, 0.9)
+    for a, b, nm in zip(lat.fields(), plain.fields(), 'f rho u'.split()):
+        assert_parity(a, b, f'continued {nm}')
+    # not pipelined (option off): same answer through the three calls
+    lat.set_option('streamed', 0)
+    out2 = lat.run_host(f, rho, u, 1.23, steps)
+    for a, b, nm in zip(out2, ref, 'f rho u'.split()):
+        assert_parity(a, b, f'unstreamed {nm}')
+    lat.close()
+    plain.close()
+
+
 def test_options_and_state_errors(P, oracle):
     from lattice_boltzmann_parallel_solver_b200 import _native as N
     from lattice_boltzmann_parallel_solver_b200.engine import Lattice
