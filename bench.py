@@ -814,13 +814,17 @@ def run_e2e(args, lat, world, rank, nx_local, ny, prof, barrier):
     barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    if g == 0:
-        # one lattice, no ghost rows: the whole job in ONE call of the public API (Lattice.run_host -> lbm_run_host): upload,
-        # time-skewed passes and download are pipelined over 256 MB row chunks, results land in the input arrays
+    streamed = True
+    try:
+        # the whole job in ONE call of the public API (Lattice.run_host -> lbm_run_host): upload, time-skewed passes and
+        # download are pipelined over 256 MB row chunks (slabs: the rows near the edges last, in lockstep with the
+        # neighbours), results land in the input arrays
         lat.run_host(hf, hr, hu, OMEGA, K, out=(hf, hr, hu))     # H2D + D2H: 96 B per cell each way
         for k in range(K):
             sink[...] = lat.probe_read(k + 1, 1)      # D2H: 16 B of every step, from the host-mapped ring
-    else:
+    except N.LbmStateError:
+        streamed = False
+    if not streamed:
         lat.load(hf, hr, hu, OMEGA)                   # H2D: 96 B per cell
         barrier()
         lat.run(K)
@@ -840,7 +844,7 @@ def run_e2e(args, lat, world, rank, nx_local, ny, prof, barrier):
             'job': f'upload f,rho,u from pinned host memory ({cells * 96 / 1e9:.1f} GB per GPU), {K} steps, '
                    f'the 16-byte probe sample of every step read by the host from a host-mapped ring, download f,rho,u'
                    + (' — one call of Lattice.run_host: upload, time-skewed passes and download pipelined over 256 MB row chunks'
-                      if g == 0 else ' — load, run, fields (slabs with ghost rows are not pipelined)')
+                      if streamed else ' — load, barrier, run, fields (not pipelined on this lattice)')
                    + f'; wall clock {dt:.2f} s, max over ranks',
             'steps': K}
 

@@ -190,8 +190,12 @@ int lbm_sync(lbm_ctx *ctx);
  * arrays and look at host arrays when they are done: :121-129, :322-327, :756-767). Output pointers may be NULL or alias
  * the inputs. On a fluid lattice without ghost rows the three phases are pipelined over row chunks (time-skewed passes:
  * rows [s_p, X - s_p) of time level p are computable as soon as rows [0, X) have arrived), so that the upload of chunk
- * c+1, the passes over chunk c and the download of the rows chunk c completed overlap on three streams; other lattices
- * take the three calls one after the other. Synchronous. */
+ * c+1, the passes over chunk c and the download of the rows chunk c completed overlap on three streams. Slabs with
+ * >= steps-per-pass ghost rows and connected neighbours are pipelined too: arrays are the padded local arrays, the
+ * interior rows are written; the rows near the slab edges are finished last, pass by pass in lockstep with the
+ * neighbours (every rank calls lbm_run_host with the same n_steps; a process-group barrier BEFORE the call, none
+ * inside: the upload phase publishes a halo epoch of its own). Other lattices take the three calls one after the
+ * other (LBM_ERR_STATE with remote neighbours, where a barrier would be needed in between). Synchronous. */
 int lbm_run_host(lbm_ctx *ctx, const double *f, const double *rho, const double *u, double omega, int n_steps,
                  double *f_out, double *rho_out, double *u_out);
 /* Number of reference steps taken since the last upload / init. */

@@ -3148,6 +3148,18 @@ extern "C" int lbm_materialize(lbm_ctx *c, double *f, double *rho, double *u)
     return lbm_materialize_region(c, 0, c->NX, 0, c->NY, f, rho, u);
 }
 
+// Publishes a halo epoch on its own (after the upload phase of a streamed run: every ghost store of the first collisions
+// is complete when this kernel starts — stream order — and visible to the peers after the system-scope fence).
+__global__ void k_halo_publish(const __grid_constant__ StepParams P)
+{
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        for (int s = 0; s < 9; s++)
+            if (P.flag_out[s]) *(volatile unsigned *)P.flag_out[s] = P.signal_value;
+        __threadfence_system();
+    }
+}
+
 // ---- whole job from and to host memory, streamed ---------------------------------------------------------------
 // lbm_run_host = lbm_upload + lbm_step(n) + lbm_materialize, same bits, same final state of the context — but on a fluid
 // lattice without ghosts the three phases are PIPELINED over row chunks (time-skewed passes): as soon as rows [0, X) of
@@ -3196,12 +3208,20 @@ extern "C" int lbm_run_host(lbm_ctx *c, const double *f, const double *rho, cons
     const int D = fused_ok(c) ? max_depth(c) : 1;
     long long chunk_rows = c->stage_cells / c->NY;
     if (c->streamed_chunk_rows > 0) chunk_rows = std::min<long long>(chunk_rows, c->streamed_chunk_rows);   // (tests)
-    const bool streamed = c->use_streamed && D >= 2 && !c->has_bc && !c->gx && !c->gy && !c->halo_ready && (long long)c->NX >= 2LL * (n_steps + D) + 2 * chunk_rows &&
-                          chunk_rows >= 8;
+    // fluid lattices: one block with in-kernel periodic wrap, or a slab with >= D ghost rows whose neighbours are connected
+    const int g = c->gx;
+    const bool streamed = c->use_streamed && D >= 2 && !c->has_bc && !c->gy && (g == 0 ? !c->halo_ready : (g >= D && c->halo_ready)) &&
+                          (long long)c->NX >= 2LL * (n_steps + D) + 2 * chunk_rows + 4LL * g && chunk_rows >= 8;
     if (!streamed) {   // every other lattice: the three calls
+        if (c->any_remote)
+            return fail(LBM_ERR_STATE, "lbm_run_host: this lattice has remote halo neighbours and cannot take the pipelined schedule "
+                                       "(needs a fluid slab with >= %d ghost rows and nx >= %lld): use lbm_upload, a process-group barrier, "
+                                       "lbm_step and lbm_materialize_region", D, 2LL * (n_steps + D) + 2 * chunk_rows + 4LL * g);
         if (int rc = lbm_upload(c, f, rho, u, omega)) return rc;
         if (int rc = lbm_step(c, omega, n_steps)) return rc;
         if (!f_out && !rho_out && !u_out) return LBM_OK;
+        if (g >= 2) return lbm_materialize_region(c, g, c->NX - g, 0, c->NY, f_out ? f_out + (size_t)g * c->NY * 9 : nullptr,
+                                                  rho_out ? rho_out + (size_t)g * c->NY : nullptr, u_out ? u_out + (size_t)g * c->NY * 2 : nullptr);
         return lbm_materialize(c, f_out, rho_out, u_out);
     }
     // pass plan: the schedule lbm_step would take
@@ -3233,6 +3253,8 @@ extern "C" int lbm_run_host(lbm_ctx *c, const double *f, const double *rho, cons
     }
     const bool want_out = f_out || rho_out || u_out;
     int out_k = 0, n_out = 0;
+    const int I0 = g, I1 = NX - g;            // the rows this rank computes
+    const bool remote = g && c->any_remote;
 
     // pass p (1-based) over lattice rows [lo, hi) and, optionally, a second range [lo2, hi2)
     auto run_pass = [&](int p, int lo, int hi, int lo2, int hi2) -> int {
@@ -3314,16 +3336,58 @@ extern "C" int lbm_run_host(lbm_ctx *c, const double *f, const double *rho, cons
         Q.in_u = R.in_u[k];
         if (int rc = first_collide(c, Q, X0, X1 - X0)) return rc;
         CK(cudaEventRecord(R.in_free[k], c->stream));
-        // level p is now computable on rows [s_p, X1 - s_p); new with this chunk: from X0 - s_p on
+        // level p is now computable on rows [I0 + lag_p, min(X1, I1) - lag_p); new with this chunk: from X0 - lag_p on
         for (int p = 1; p <= NP; p++)
-            if (int rc = run_pass(p, std::max(X0 - lag[p], lag[p]), X1 - lag[p], 0, 0)) return rc;
-        if (int rc = emit_rows(std::max(X0 - sP, sP), X1 - sP)) return rc;
+            if (int rc = run_pass(p, std::max(X0 - lag[p], I0 + lag[p]), std::min(X1, I1) - lag[p], 0, 0)) return rc;
+        if (int rc = emit_rows(std::max(X0 - sP, I0 + sP), std::min(X1, I1) - sP)) return rc;
     }
-    // the periodic seam: rows [NX - lag_p, NX) and [0, lag_p) of level p, in pass order; then their results
-    for (int p = 1; p <= NP; p++)
-        if (int rc = run_pass(p, NX - lag[p], NX, 0, lag[p])) return rc;
-    if (int rc = emit_rows(NX - sP, NX)) return rc;
-    if (int rc = emit_rows(0, sP)) return rc;
+    if (!g) {
+        // the periodic seam: rows [NX - lag_p, NX) and [0, lag_p) of level p, in pass order
+        for (int p = 1; p <= NP; p++)
+            if (int rc = run_pass(p, NX - lag[p], NX, 0, lag[p])) return rc;
+    } else {
+        // Slab: the rows within lag_p of the slab edges. Everything so far touched neither my ghost rows nor the
+        // neighbours' — except the first collisions, which stored the edge rows of S_0 into the neighbours' ghost rows:
+        // publish that (one epoch), then take the passes in lockstep with the neighbours: the g rows next to each edge by
+        // the HALO launch (waits for the neighbours' previous pass, stores into their ghost rows, publishes), the rest plain.
+        if (remote) {
+            StepParams Pp;
+            fill_common(c, Pp, 1, 0, omega);
+            fill_halo(c, Pp, 0, true);
+            Pp.signal_value = c->halo_epoch + 1;
+            k_halo_publish<<<1, 32, 0, c->stream>>>(Pp);
+            CK(cudaGetLastError());
+            c->halo_epoch++;
+        }
+        for (int p = 1; p <= NP; p++) {
+            const int d = depth[p - 1];
+            StepParams Pe;
+            fill_common(c, Pe, (p - 1) & 1, p & 1, omega);
+            fill_halo(c, Pe, p & 1, true);
+            if (probe) {
+                Pe.px = c->px;
+                Pe.py = c->py;
+                Pe.probe = c->probe;
+                Pe.progress = c->progress;
+                Pe.probe_cap = c->probe_cap;
+                Pe.tc_in = R.tclock + (p - 1);
+                Pe.tc_out = R.tclock + p;
+            }
+            if (remote) {
+                Pe.wait_value = c->halo_epoch;
+                Pe.signal_value = c->halo_epoch + 1;
+            }
+            if (d >= 2) {
+                if (int rc = fused_launch<true>(c, Pe, I0, g, I1 - g, g, g, c->stream, d)) return rc;
+            } else {
+                if (int rc = rows_launch(c, Pe, I0, g, I1 - g, g, false, true, c->stream)) return rc;
+            }
+            if (remote) c->halo_epoch++;
+            if (int rc = run_pass(p, I0 + g, I0 + lag[p], I1 - lag[p], I1 - g)) return rc;
+        }
+    }
+    if (int rc = emit_rows(I1 - sP, I1)) return rc;
+    if (int rc = emit_rows(I0, I0 + sP)) return rc;
     // the context is now where lbm_upload + lbm_step(n_steps) would have left it
     c->cur = NP & 1;
     c->t = n_steps;

@@ -83,15 +83,28 @@ def main():
         lat.set_option('fused_depth', depth)
         halo = PU.communication(comm.Create_cart(dims=[k, 1], periods=[True, True]))
         halo.attach(lat)
-        lat.load(padded(f, rank, g), padded(rho, rank, g), padded(u, rank, g), omega)
-        comm.Barrier()
-        for chunk in (7, 6):              # 7: passes + a one-step launch; 6: ends on a pass (FINAL-mode materialisation)
-            lat.run(chunk)
-        lat.sync()
+        if '--run-host' in sys.argv:
+            # the whole job in one call, pipelined over row chunks; the slab edges are finished last, in lockstep
+            lat.set_option('streamed_chunk_rows', 300)
+            comm.Barrier()
+            pf, pr, pu = padded(f, rank, g), padded(rho, rank, g), padded(u, rank, g)
+            l0 = lat.launches
+            out = lat.run_host(pf, pr, pu, omega, steps)
+            assert lat.launches - l0 > 2 * (n // 300), 'the pipelined schedule was not taken'
+            for a, b, nm in zip(out, ref, 'f rho u'.split()):
+                assert np.array_equal(a[g:n + g], b[rank * n:(rank + 1) * n]), f'slab {rank}: run_host {nm} differs from the oracle'
+            comm.Barrier()
+        else:
+            lat.load(padded(f, rank, g), padded(rho, rank, g), padded(u, rank, g), omega)
+            comm.Barrier()
+            for chunk in (7, 6):          # 7: passes + a one-step launch; 6: ends on a pass (FINAL-mode materialisation)
+                lat.run(chunk)
+            lat.sync()
         check(lat, rank, g)
         comm.Barrier()
         if rank == 0:
-            print(f'OK {k} slabs, one process per GPU' + (' (shared)' if shared else '') + f', depth {depth}', flush=True)
+            print(f'OK {k} slabs, one process per GPU' + (' (shared)' if shared else '') + f', depth {depth}' +
+                  (', run_host' if '--run-host' in sys.argv else ''), flush=True)
         lat.close()
 
 

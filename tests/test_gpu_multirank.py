@@ -178,3 +178,14 @@ def test_karman_slabs_two_steps_per_pass_across_ranks(size):
     place = _placement(size)
     out = _torchrun('mp_karman_slabs.py', size, 29580 + size, *place)
     assert f'OK {size} karman slabs' in out
+
+
+@pytest.mark.parametrize('size,depth', [(2, 3), (4, 3), (2, 2)])
+def test_streamed_run_on_slabs_across_ranks(size, depth):
+    """lbm_run_host on slabs: upload, time-skewed passes and download pipelined over row chunks on every rank; the rows
+    near the slab edges are finished last, pass by pass with ghost stores and flag handshake (the upload phase publishes
+    an epoch of its own, no host barrier inside the call). Interior rows must equal the single-block oracle, and the
+    context must hold the state of the last step (check() materialises it again)."""
+    place = _placement(size)
+    out = _torchrun('mp_slabs.py', size, 29640 + size + depth, '--depth', str(depth), '--run-host', *place)
+    assert f'OK {size} slabs, one process per GPU' + (' (shared)' if place else '') + f', depth {depth}, run_host' in out
