@@ -310,12 +310,12 @@ def bind_to_gpu_numa_node(gpu):
 
 
 def source_sha():
-    """sha256 of the hot kernels' source (the marked region of lbm_b200.cu: k_step_pair, k_step2x, k_stepNx, and the
+    """sha256 of the hot kernels' source (the marked region of lbm_kernels.cuh: k_step_pair, k_step2x, k_stepNx, and the
     arithmetic header): profiles/traffic.json is only quoted for the kernels it was captured on."""
     import hashlib
     h = hashlib.sha256()
     csrc = os.path.join(ROOT, 'lattice_boltzmann_parallel_solver_b200', 'csrc')
-    with open(os.path.join(csrc, 'lbm_b200.cu'), 'rb') as fh:
+    with open(os.path.join(csrc, 'lbm_kernels.cuh'), 'rb') as fh:
         text = fh.read()
     a, b = text.find(b'// ==== HOT KERNELS BEGIN'), text.find(b'// ==== HOT KERNELS END')
     h.update(text[a:b] if 0 <= a < b else text)

@@ -5,7 +5,8 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, 'csrc', 'lbm_b200.cu')
-DEPS = [SRC, os.path.join(HERE, 'csrc', 'lbm_device.cuh'), os.path.join(os.path.dirname(HERE), 'include', 'lbm_b200.h')]
+DEPS = [SRC, os.path.join(HERE, 'csrc', 'lbm_kernels.cuh'), os.path.join(HERE, 'csrc', 'lbm_device.cuh'),
+        os.path.join(os.path.dirname(HERE), 'include', 'lbm_b200.h')]
 OUT = os.path.join(HERE, 'liblbm_b200.so')
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
