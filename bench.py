@@ -468,9 +468,9 @@ def main():
             lat = karman_lattice(nx_local, ny, bc_mode)
         elif workload == 'karman':
             # N GPUs: the rule set on the GLOBAL (nx_local * N) x ny lattice, slabs with two ghost rows that carry the
-            # neighbour's kinds; two steps per pass on every rank (fluid two-step kernel + strip windows next to boundary
+            # neighbour's kinds; `depth` steps per pass on every rank (multi-step kernel + strip windows next to boundary
             # rows and slab edges)
-            g = 2
+            g = max(depth, 2)
             km = karman_slab_kind_map(nx_local * world, ny, rank * nx_local - g, nx_local + 2 * g)
             lat = Lattice(nx_local + 2 * g, ny, km, ghost=(g, 0), bc_mode=bc_mode)
             cart = ldist.comm_world().Create_cart(dims=[world, 1], periods=[True, True])
@@ -486,7 +486,7 @@ def main():
             par.communication(cart).attach(lat)
         if depth == 1:
             lat.set_option('fused', 0)
-        elif workload != 'karman':
+        else:
             lat.set_option('fused_depth', depth)
         return lat, nx_local, ny, prof
 
@@ -537,7 +537,7 @@ def main():
     # / peak — the fraction of the memory roof the kernel really uses.
     fused = depth > 1
     if fused:
-        spl = depth if args.workload != 'karman' else 2
+        spl = depth
         lat.set_option('fused_exact', 1)
         n_pure = spl * max(4, min(24, args.steps // spl))
         lat.run(spl * 2)
@@ -551,9 +551,8 @@ def main():
                   f'ring(s) of intermediate rows)')
         tkey = f'k_stepNx{depth}_dram_bytes_per_launch_16384'
         if args.workload == 'karman':
-            kernel = ('k_step2x<128> on the rows whose two-step dependency cone is all fluid + two one-step mask launches '
-                      'through a window on each strip of boundary rows (inlet/outlet rows, plate rows); duration = one pass')
-            tkey = 'k_step2x_dram_bytes_per_launch_16384'
+            kernel += (' on the rows whose dependency cone is all fluid + one one-step mask launch per step through windows on each '
+                       'strip of boundary rows (inlet/outlet rows, plate rows); duration = one pass')
     else:
         launch_ms = ms / args.steps
         algo_launch = per_gpu_cells * ALGO_BYTES_PER_UPDATE
@@ -626,7 +625,7 @@ def main():
         karman_rec = sub_record('karman', False, args.size, max(8, min(args.steps, 60)), max(3, min(args.warmup, 12)))
         karman_rec['scaling'] = 'weak'
         karman_rec['workload'] = (f'von Karman rule set (inlet row, outlet rows, plate of ny/4.5 at nx/4; nu 0.04, u_in 0.1) on the '
-                                  f'global {args.size * world}x{args.size} lattice ({args.size}x{args.size} per GPU), two steps per '
+                                  f'global {args.size * world}x{args.size} lattice ({args.size}x{args.size} per GPU), {depth} steps per '
                                   f'pass: the BC-bearing case of SURVEY.md section 8(d)')
         karman_rec['vs_periodic'] = karman_rec['value'] / mlups if 'value' in karman_rec else None
 
@@ -839,7 +838,39 @@ def run_e2e(args, lat, world, rank, nx_local, ny, prof, barrier):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
     total_cells = nx_local * world * ny
-    return {'value': total_cells * K / dt / 1e6, 'unit': 'MLUPS',
+    # What the box's host<->device links sustain when every rank copies in both directions at once (outside the timed
+    # region; plain pinned-memory copies on two streams, 2 GB each way per rank): the floor under the e2e wall clock.
+    link = None
+    try:
+        nb = min(2 << 30, hf.nbytes // 2) // 8
+        src = torch.from_numpy(hf.reshape(-1)[:nb])
+        dst_h = torch.from_numpy(hf.reshape(-1)[nb:2 * nb])
+        d_in = torch.empty(nb, dtype=torch.float64, device='cuda')
+        d_out = torch.zeros(nb, dtype=torch.float64, device='cuda')
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        for rep in range(2):                      # first repetition: warm-up
+            torch.cuda.synchronize()
+            barrier()
+            t1 = time.perf_counter()
+            with torch.cuda.stream(s1):
+                d_in.copy_(src, non_blocking=True)
+            with torch.cuda.stream(s2):
+                dst_h.copy_(d_out, non_blocking=True)
+            torch.cuda.synchronize()
+            tl = time.perf_counter() - t1
+        if world > 1:
+            t = torch.tensor([tl], device='cuda')
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tl = float(t.item())
+        rate = 2 * nb * 8 * world / tl / 1e9      # GB/s, both directions, all ranks
+        moved = cells * 96.0 * 2 * world / 1e9
+        link = {'both_directions_all_ranks_gbs': rate, 'per_gpu_each_way_gbs': rate / 2 / world,
+                'e2e_bytes_gb': moved, 'e2e_floor_s': moved / rate, 'e2e_wall_s': dt, 'fraction_of_floor': moved / rate / dt,
+                'how': f'{world} rank(s) x (2 GB host->device + 2 GB device->host, pinned memory, concurrently on two streams), max over ranks'}
+        del d_in, d_out
+    except Exception as e:   # never let a diagnostic break the line
+        link = {'skipped': str(e)[:120]}
+    return {'value': total_cells * K / dt / 1e6, 'unit': 'MLUPS', 'link_probe': link,
             'h2d_bytes_per_step': cells * 96.0 / K, 'd2h_bytes_per_step': cells * 96.0 / K + 16.0,
             'job': f'upload f,rho,u from pinned host memory ({cells * 96 / 1e9:.1f} GB per GPU), {K} steps, '
                    f'the 16-byte probe sample of every step read by the host from a host-mapped ring, download f,rho,u'

@@ -88,15 +88,17 @@ struct lbm_ctx {
     uint8_t *kind_map = nullptr;
     lbm_kind *kinds = nullptr;
     double *ktab = nullptr, *ctab = nullptr;
-    double *outbuf[3] = {nullptr, nullptr, nullptr};   // outlet side buffers of S[0], S[1] and of the strips' intermediate state
+    double *outbuf[4] = {nullptr, nullptr, nullptr, nullptr};   // outlet side buffers of S[0], S[1] and of the strips' windows (2: the last one, 3: the first of three-step passes)
     double *snap_row = nullptr, *snap_col = nullptr;
     // Two steps per pass on lattices WITH boundary cells (plan_strips): rows whose two-step dependency cone holds
     // fluid cells only go through k_step2x; the few others are advanced by two one-step mask launches through a
     // window that holds the intermediate state S_{t+1} of the strip (+ one row each side).
     struct Strip {
         int a, b;              // output rows [a, b), unwrapped: 0 <= a < NX, b may exceed NX (periodic wrap)
-        double *buf;           // [9][b - a + 2][pitch]: rows a-1 .. b of S_{t+1}
+        double *buf;           // [9][b - a + 2][pitch]: rows a-1 .. b of the LAST intermediate state (S_{t+1} of a two-step, S_{t+2} of a three-step pass)
+        double *buf1;          // [9][b - a + 4][pitch]: rows a-2 .. b+1 of S_{t+1} of a three-step pass (null when planned for two steps)
     };
+    int bc_depth = 2;          // steps per pass the strips were planned for (reach of a boundary row: +- bc_depth rows)
     std::vector<Strip> strips;
     std::vector<std::pair<int, int>> clean;   // row ranges [first, last) of k_step2x
     bool fused_bc = false;
@@ -117,7 +119,7 @@ struct lbm_ctx {
     int px = -1, py = -1, probe_cap = 0;
     double *probe = nullptr;         // cudaHostAlloc (mapped): written by the probe cell's thread, read by the host
     long long *progress = nullptr;   // cudaHostAlloc (mapped)
-    long long *tcount = nullptr;   // device [3]: time of the state in S[0], S[1], and in the strip windows
+    long long *tcount = nullptr;   // device [4]: time of the state in S[0], S[1], and in the strip windows (2: last, 3: first of three)
     // CUDA graphs of kGraphSteps steps for launch-bound lattices, keyed by (omega, parity, probe, bc mode)
     struct GraphEntry {
         double omega;
@@ -442,9 +444,11 @@ extern "C" int lbm_destroy(lbm_ctx *c)
     drop_graphs(c);
     for (int s = 0; s < 9; s++)
         if (c->peer[s].mapped) ipc_release(c->peer[s].mapped);   // every slot holds its own reference
-    for (auto &s : c->strips)
+    for (auto &s : c->strips) {
         if (s.buf) cudaFree(s.buf);
-    void *bufs[] = {c->arena,  c->kind_map, c->kinds,    c->ktab,   c->ctab,  c->outbuf[0],   c->outbuf[1], c->outbuf[2], c->cells, c->snap_row, c->snap_col,
+        if (s.buf1) cudaFree(s.buf1);
+    }
+    void *bufs[] = {c->arena,  c->kind_map, c->kinds,    c->ktab,   c->ctab,  c->outbuf[0],   c->outbuf[1], c->outbuf[2], c->outbuf[3], c->cells, c->snap_row, c->snap_col,
                     c->done_counter, c->err_flag, c->stage_f, c->stage_rho, c->stage_u, c->mm_acc, c->tcount};
     for (void *b : bufs)
         if (b) cudaFree(b);
@@ -489,7 +493,7 @@ extern "C" int lbm_destroy(lbm_ctx *c)
 // which on a lattice with boundary cells is done by the one-step mask kernel (k_step2x knows neither rules nor halos
 // ... the fluid edge launch of two_steps() does, but not next to boundary cells; one code path is enough here).
 static bool plan_rows_slab(int NX, int gx, const std::vector<char> &dirty, std::vector<std::pair<int, int>> &strips,
-                           std::vector<std::pair<int, int>> &clean)
+                           std::vector<std::pair<int, int>> &clean, int reach = 2)
 {
     strips.clear();
     clean.clear();
@@ -498,7 +502,7 @@ static bool plan_rows_slab(int NX, int gx, const std::vector<char> &dirty, std::
     std::vector<char> strip_row(NX, 0);
     int n_strip_rows = 0;
     for (int x = lo; x < hi; x++) {
-        for (int d = -2; d <= 2; d++) strip_row[x] |= dirty[x + d];
+        for (int d = -reach; d <= reach; d++) strip_row[x] |= dirty[x + d];
         if (x < lo + gx || x >= hi - gx) strip_row[x] = 1;
         n_strip_rows += strip_row[x];
     }
@@ -513,7 +517,7 @@ static bool plan_rows_slab(int NX, int gx, const std::vector<char> &dirty, std::
 }
 
 static bool plan_rows(int NX, const std::vector<char> &dirty, std::vector<std::pair<int, int>> &strips,
-                      std::vector<std::pair<int, int>> &clean)
+                      std::vector<std::pair<int, int>> &clean, int reach = 2)
 {
     strips.clear();
     clean.clear();
@@ -521,7 +525,7 @@ static bool plan_rows(int NX, const std::vector<char> &dirty, std::vector<std::p
     std::vector<char> strip_row(NX, 0);
     int n_strip_rows = 0;
     for (int x = 0; x < NX; x++) {
-        for (int d = -2; d <= 2; d++) strip_row[x] |= dirty[((x + d) % NX + NX) % NX];
+        for (int d = -reach; d <= reach; d++) strip_row[x] |= dirty[((x + d) % NX + NX) % NX];
         n_strip_rows += strip_row[x];
     }
     if (2 * n_strip_rows > NX) return false;   // mostly boundary rows (walls along x, ...): one step per pass
@@ -568,20 +572,25 @@ extern "C" int lbm_plan_two_step(int nx, const uint8_t *row_has_boundary, int *n
 
 static int plan_strips(lbm_ctx *c, const std::vector<char> &dirty)
 {
+    // planned for the deepest pass this lattice may take (a shallower pass can use the same, wider strips)
+    const int reach = std::max(2, std::min(3, c->gx ? std::min(c->gx, c->fused_depth) : c->fused_depth));
     std::vector<std::pair<int, int>> rows, clean;
-    if (!(c->gx ? plan_rows_slab(c->NX, c->gx, dirty, rows, clean) : plan_rows(c->NX, dirty, rows, clean))) return LBM_OK;
+    if (!(c->gx ? plan_rows_slab(c->NX, c->gx, dirty, rows, clean, reach) : plan_rows(c->NX, dirty, rows, clean, reach))) return LBM_OK;
     for (const auto &r : rows) {
-        lbm_ctx::Strip s = {r.first, r.second, nullptr};
-        const size_t bytes = (size_t)9 * (s.b - s.a + 2) * c->pitch * 8;
-        if (cudaMalloc(&s.buf, bytes) != cudaSuccess) {
+        lbm_ctx::Strip s = {r.first, r.second, nullptr, nullptr};
+        const size_t bytes = (size_t)9 * (s.b - s.a + 2) * c->pitch * 8, bytes1 = (size_t)9 * (s.b - s.a + 4) * c->pitch * 8;
+        if (cudaMalloc(&s.buf, bytes) != cudaSuccess || (reach == 3 && cudaMalloc(&s.buf1, bytes1) != cudaSuccess)) {
             cudaGetLastError();
-            return fail(LBM_ERR_NOMEM, "cannot allocate %.1f MB for a boundary strip window", bytes / 1e6);
+            if (s.buf) cudaFree(s.buf);
+            return fail(LBM_ERR_NOMEM, "cannot allocate %.1f MB for a boundary strip window", (bytes + bytes1) / 1e6);
         }
         c->strips.push_back(s);   // owned by the context from here on (lbm_destroy frees it)
         CK(cudaMemsetAsync(s.buf, 0, bytes, c->stream));
+        if (s.buf1) CK(cudaMemsetAsync(s.buf1, 0, bytes1, c->stream));
     }
     c->clean = clean;
     c->fused_bc = true;
+    c->bc_depth = reach;
     return LBM_OK;
 }
 
@@ -630,13 +639,13 @@ static int ctx_build(lbm_ctx *c, const lbm_bc_desc *bc)
     CK(cudaMemsetAsync(c->done_counter, 0, 8, c->stream));
     CK(cudaMemsetAsync(c->err_flag, 0, 4, c->stream));
     CK(cudaMalloc(&c->mm_acc, 32));
-    CK(cudaMalloc(&c->tcount, 24));
-    CK(cudaMemsetAsync(c->tcount, 0, 24, c->stream));
+    CK(cudaMalloc(&c->tcount, 32));
+    CK(cudaMemsetAsync(c->tcount, 0, 32, c->stream));
     CK(cudaHostAlloc((void **)&c->progress, 64, cudaHostAllocMapped));
     *c->progress = 0;
     CK(cudaHostAlloc((void **)&c->err_host, 64, cudaHostAllocMapped));
     *c->err_host = 0;
-    for (int b = 0; b < 3; b++) {
+    for (int b = 0; b < 4; b++) {
         CK(cudaMalloc(&c->outbuf[b], (size_t)3 * c->pitch * 8));
         CK(cudaMemsetAsync(c->outbuf[b], 0, (size_t)3 * c->pitch * 8, c->stream));
     }
@@ -1035,8 +1044,8 @@ static bool tail_free(const lbm_ctx *) { return true; }
 // further than their ghost rows.
 static int max_depth(const lbm_ctx *c)
 {
-    if (c->has_bc) return 2;
-    return c->gx ? std::min(c->gx, c->fused_depth) : c->fused_depth;
+    const int d = c->gx ? std::min(c->gx, c->fused_depth) : c->fused_depth;
+    return c->has_bc ? std::min(d, c->bc_depth) : d;   // strips are planned for bc_depth steps (or fewer) per pass
 }
 
 // Output rows per thread block of the multi-step kernels. Every block recomputes D-1 intermediate rows per level at each
@@ -1113,12 +1122,13 @@ static int fused_launch(lbm_ctx *c, StepParams P, int row0a, int na, int row0b, 
     return LBM_OK;
 }
 
-// Lattice with boundary cells (plan_strips): k_step2x on the clean rows, two one-step mask launches per strip.
+// Lattice with boundary cells (plan_strips): the multi-step kernel on the clean rows, `depth` one-step mask launches per
+// strip through its windows: S_t rows [a-d, b+d) -> ... -> the last window (rows [a-1, b+1) of S_{t+d-1}) -> S_{t+d} rows [a, b).
 // All launches read S[src] (and the strip windows) and write disjoint rows of S[dst]: plain stream order.
-// Slabs (gx >= 2): the strips next to the slab edges are the only launches that touch ghost rows. Their first launch
-// (S_t -> window, ghost row gx-1 / NX-gx included) waits for the neighbours' previous pass; their second launch stores
-// the rows within gx of the edge into the neighbours' ghost rows as well, and the last of them publishes the pass.
-static int two_steps_bc(lbm_ctx *c, const StepParams &P0, int src, int dst)
+// Slabs (gx >= depth): the strips next to the slab edges are the only launches that touch ghost rows. Their first launch
+// (ghost rows included) waits for the neighbours' previous pass; their last launch stores the rows within gx of the
+// edge into the neighbours' ghost rows as well, and the last of them publishes the pass.
+static int two_steps_bc(lbm_ctx *c, const StepParams &P0, int src, int dst, int depth)
 {
     const int NX = c->NX;
     const bool probe = c->probe && c->px >= 0;
@@ -1128,8 +1138,8 @@ static int two_steps_bc(lbm_ctx *c, const StepParams &P0, int src, int dst)
         StepParams P = P0;
         const auto ra = c->clean[i], rb = i + 1 < c->clean.size() ? c->clean[i + 1] : std::make_pair(0, 0);
         if (probe && ((c->px >= ra.first && c->px < ra.second) || (c->px >= rb.first && c->px < rb.second))) set_probe(c, P, src, dst);
-        // (a redo with a new omega for the last collision needs the kernel that knows omega_last: k_stepNx<2>)
-        if (int rc = fused_launch<false>(c, P, ra.first, ra.second - ra.first, rb.first, rb.second - rb.first, pick_seg(c, c->NX), c->stream, 2,
+        // (a redo with a new omega for the last collision needs the kernel that knows omega_last: k_stepNx)
+        if (int rc = fused_launch<false>(c, P, ra.first, ra.second - ra.first, rb.first, rb.second - rb.first, pick_seg(c, c->NX, depth), c->stream, depth,
                                          P0.omega_last != P0.omega)) return rc;
     }
     int last_edge = -1;
@@ -1138,8 +1148,6 @@ static int two_steps_bc(lbm_ctx *c, const StepParams &P0, int src, int dst)
     for (size_t i = 0; i < c->strips.size(); i++) {
         const auto &s = c->strips[i];
         const bool edge = slab && (s.a == c->gx || s.b == NX - c->gx);
-        const int base = (s.a + NX - 1) % NX;
-        const long long wplane = (long long)(s.b - s.a + 2) * c->pitch;
         const bool probe_here = probe && ((c->px >= s.a && c->px < s.b) || (c->px + NX >= s.a && c->px + NX < s.b));
         // rows [lo, hi) of the lattice, unwrapped, as (at most) two wrapped ranges
         auto launch_rows = [&](StepParams &P, int lo, int hi) {
@@ -1147,32 +1155,48 @@ static int two_steps_bc(lbm_ctx *c, const StepParams &P0, int src, int dst)
             if (hi > NX) return rows_launch(c, P, lo, NX - lo, 0, hi - NX, true, edge, c->stream);
             return rows_launch(c, P, lo, hi - lo, 0, 0, true, edge, c->stream);
         };
-        StepParams P1 = P0;   // S_t -> window: rows a-1 .. b of S_{t+1}
-        P1.dst = s.buf;
-        P1.dplane = wplane;
-        P1.dbase = base;
-        P1.out_next = c->outbuf[2];
-        P1.no_snap = 1;
-        if (edge) {           // reads ghost rows: wait for the neighbours; an intermediate state is never stored into theirs
-            fill_halo(c, P1, dst, true);
-            for (int k = 0; k < 9; k++) P1.halo[k].base = nullptr;
-            if (remote) P1.wait_value = E;
+        // stage k = 1 .. depth reads stage k-1's buffer (0: S[src]) and writes stage k's (depth: S[dst]); the windows of a
+        // three-step pass are buf1 (rows a-2 ..) then buf (rows a-1 ..), a two-step pass uses buf only
+        for (int k = 1; k <= depth; k++) {
+            const int m_in = depth - (k - 1), m_out = depth - k;           // margins: rows [a - m, b + m)
+            StepParams P = P0;
+            auto window = [&](int m, double *&ptr, long long &plane, int &base, int &ob, int &tc) {
+                ptr = m == 1 ? s.buf : s.buf1;
+                plane = (long long)(s.b - s.a + 2 * m) * c->pitch;
+                base = (s.a + NX - m) % NX;
+                ob = m == 1 ? 2 : 3;
+                tc = m == 1 ? 2 : 3;
+            };
+            int tc_in = src, tc_out = dst;
+            if (k > 1) {
+                double *ptr; long long plane; int base, ob;
+                window(m_in, ptr, plane, base, ob, tc_in);
+                P.src = ptr;
+                P.plane = plane;
+                P.sbase = base;
+                P.out_cur = c->outbuf[ob];
+            }
+            if (k < depth) {
+                double *ptr; long long plane; int base, ob;
+                window(m_out, ptr, plane, base, ob, tc_out);
+                P.dst = ptr;
+                P.dplane = plane;
+                P.dbase = base;
+                P.out_next = c->outbuf[ob];
+            } else {
+                P.omega = P0.omega_last;     // the pass's LAST collision (differs when the caller changed omega)
+            }
+            P.no_snap = 1;
+            if (edge) {   // ghost rows: wait before the first stage, store into the neighbours' and publish in the last
+                fill_halo(c, P, dst, true);
+                if (k < depth)
+                    for (int q = 0; q < 9; q++) P.halo[q].base = nullptr;
+                if (remote && k == 1) P.wait_value = E;
+                if (remote && k == depth && (int)i == last_edge) P.signal_value = E + 1;
+            }
+            if (probe_here) set_probe(c, P, tc_in, tc_out);
+            if (int rc = launch_rows(P, s.a - m_out, s.b + m_out)) return rc;
         }
-        if (probe_here) set_probe(c, P1, src, 2);
-        if (int rc = launch_rows(P1, s.a - 1, s.b + 1)) return rc;
-        StepParams P2 = P0;   // window -> S_{t+2} rows a .. b-1
-        P2.src = s.buf;
-        P2.plane = wplane;
-        P2.sbase = base;
-        P2.out_cur = c->outbuf[2];
-        P2.omega = P0.omega_last;
-        P2.no_snap = 1;
-        if (edge) {
-            fill_halo(c, P2, dst, true);
-            if (remote && (int)i == last_edge) P2.signal_value = E + 1;
-        }
-        if (probe_here) set_probe(c, P2, 2, dst);
-        if (int rc = launch_rows(P2, s.a, s.b)) return rc;
     }
     if (remote) c->halo_epoch++;
     return LBM_OK;
@@ -1184,7 +1208,7 @@ static int two_steps(lbm_ctx *c, int src, double omega, int depth = 2, double om
     StepParams P;
     fill_common(c, P, src, dst, omega);
     if (omega_last != 0.0) P.omega_last = omega_last;   // redo of a pass whose last collision must use the caller's new omega
-    if (c->has_bc) return two_steps_bc(c, P, src, dst);
+    if (c->has_bc) return two_steps_bc(c, P, src, dst, depth);
     set_probe(c, P, src, dst);
     const int g = c->gx, xlo = g, xhi = c->NX - g;
     if (!g) return fused_launch<false>(c, P, xlo, xhi - xlo, 0, 0, pick_seg(c, xhi - xlo, depth), c->stream, depth, P.omega_last != P.omega);
@@ -1247,7 +1271,7 @@ static int begin_load(lbm_ctx *c, double omega, InitParams &Q)
 
 static int end_load(lbm_ctx *c, double omega)
 {
-    CK(cudaMemsetAsync(c->tcount, 0, 24, c->stream));
+    CK(cudaMemsetAsync(c->tcount, 0, 32, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     *c->progress = 0;
     c->loaded = true;
@@ -1640,8 +1664,8 @@ static int materialize_rows(lbm_ctx *c, int x0, int x1, int y0, int y1, double *
             return cudaGetLastError();
         };
         if (c->last_depth > 1 && c->has_bc) {
-            // lattice with boundary cells after a two-step pass: clean rows as above; strip rows from their WINDOW, which still
-            // holds S_{t-1} of the strip (+ one row each side) from the pass's first launch — one FINAL mask launch
+            // lattice with boundary cells after a multi-step pass: clean rows as above; strip rows from their last WINDOW, which
+            // still holds S_{t-1} of the strip (+ one row each side) — one FINAL mask launch
             auto owner = [&](int x) -> const lbm_ctx::Strip * {   // the strip that holds lattice row x (strips may wrap), or null
                 for (const auto &st : c->strips)
                     if ((x >= st.a && x < st.b) || (x + c->NX >= st.a && x + c->NX < st.b)) return &st;
@@ -1663,7 +1687,7 @@ static int materialize_rows(lbm_ctx *c, int x0, int x1, int y0, int y1, double *
                     e = launch<true, false, true, false>(Q, (hi - lo) * P.bpr, bs, c->stream);
                     c->launches++;
                 } else {
-                    e = deep_final(P, lo, hi - lo, 2);
+                    e = deep_final(P, lo, hi - lo, c->last_depth);
                 }
                 lo = hi;
             }
@@ -1815,7 +1839,7 @@ extern "C" int lbm_run_host(lbm_ctx *c, const double *f, const double *rho, cons
     {
         std::vector<long long> tl(s.begin(), s.end());
         CK(cudaMemcpyAsync(R.tclock, tl.data(), tl.size() * 8, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemsetAsync(c->tcount, 0, 24, c->stream));
+        CK(cudaMemsetAsync(c->tcount, 0, 32, c->stream));
         CK(cudaStreamSynchronize(c->stream));   // (tl is a host temporary)
         *c->progress = 0;
     }
@@ -1963,11 +1987,11 @@ extern "C" int lbm_run_host(lbm_ctx *c, const double *f, const double *rho, cons
     c->omega = omega;
     c->loaded = true;
     {
-        long long tt[3] = {0, 0, 0};
+        long long tt[4] = {0, 0, 0, 0};
         tt[c->cur] = n_steps;
         tt[c->cur ^ 1] = n_steps - depth[NP - 1];
-        tt[2] = n_steps;
-        CK(cudaMemcpyAsync(c->tcount, tt, 24, cudaMemcpyHostToDevice, c->stream));
+        tt[2] = tt[3] = n_steps;
+        CK(cudaMemcpyAsync(c->tcount, tt, 32, cudaMemcpyHostToDevice, c->stream));
     }
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaStreamSynchronize(R.d2h));
@@ -2004,9 +2028,9 @@ extern "C" int lbm_probe_config(lbm_ctx *c, int x, int y, int capacity)
     c->py = y;
     c->probe_cap = capacity;
     // S[cur] holds time t, S[cur^1] time t-1 (the launch an omega change redoes reads it and must land on t again)
-    long long tt[3] = {c->t, c->t, c->t};
+    long long tt[4] = {c->t, c->t, c->t, c->t};
     tt[c->cur ^ 1] = c->t - 1;
-    CK(cudaMemcpyAsync(c->tcount, tt, 24, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->tcount, tt, 32, cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     drop_graphs(c);
     return LBM_OK;

@@ -143,6 +143,7 @@ class Lattice:
         rho = N.as_f64(rho, (self.nx, self.ny), 'density')
         u = N.as_f64(u, (self.nx, self.ny, 2), 'velocity')
         assert 0 < omega < 2 and n_steps >= 1
+        self.reset_for_upload()           # queued steps are launched, results still referenced are brought to the host
         if out is None:
             out = (np.empty_like(f), np.empty_like(rho), np.empty_like(u))
         for a, shape in zip(out, ((self.nx, self.ny, 9), (self.nx, self.ny), (self.nx, self.ny, 2))):

@@ -1,9 +1,9 @@
-"""The von Karman rule set (inlet row, outlet rows, plate) on slabs with TWO ghost rows: two steps per pass on every
+"""The von Karman rule set (inlet row, outlet rows, plate) on slabs with D ghost rows: D = 3 (or 2) steps per pass on every
 rank — the fluid two-step kernel on rows whose cone is all fluid, strip windows next to boundary rows and next to the
 slab edges (those launches read the ghost rows, store into the neighbours' and carry the flag handshake) — against the
 single-block C oracle on a field that varies along both axes.
 
-    torchrun --nproc-per-node K tests/mp_karman_slabs.py [--shared-gpu]
+    torchrun --nproc-per-node K tests/mp_karman_slabs.py [--depth D] [--shared-gpu]
 """
 import os
 import sys
@@ -26,7 +26,8 @@ def main():
     comm = ldist.comm_world()
     rank, k = comm.Get_rank(), comm.Get_size()
     N.set_device(0 if shared else int(os.environ.get('LOCAL_RANK', '0')))
-    ny, n, g, steps = 512, 2052, 2, 13
+    depth = int(sys.argv[sys.argv.index('--depth') + 1]) if '--depth' in sys.argv else 3
+    ny, n, g, steps = 512, 2052, depth, 13
     nxg = n * k
     omega = float(np.reciprocal(3 * 0.04 + 0.5))
     d = int(ny / 4.5) // 2 * 2
@@ -60,7 +61,7 @@ def main():
     comm.Barrier()
     if rank == 0:
         # 13 one-step launches would be >= 13 (x2 with the fix-up kernel); two-step passes: 6 passes + 1 single step
-        print(f'OK {k} karman slabs' + (' (shared)' if shared else '') + f', launches per rank {[(r, l, "fluid" if t else "bc") for r, l, t in everyone]}',
+        print(f'OK {k} karman slabs, {depth} steps per pass' + (' (shared)' if shared else '') + f', launches per rank {[(r, l, "fluid" if t else "bc") for r, l, t in everyone]}',
               flush=True)
     lat.close()
 

@@ -169,15 +169,15 @@ def test_karman_one_process_per_rank(size):
     assert f'OK {size} ranks ({"one gpu/gloo+ipc" if place else "gpu/nccl+ipc"})' in out
 
 
-@pytest.mark.parametrize('size', [2, 4, 8])
-def test_karman_slabs_two_steps_per_pass_across_ranks(size):
-    """Boundary-bearing lattices on N ranks take two steps per pass too (slabs with two ghost rows that carry the
+@pytest.mark.parametrize('size,depth', [(2, 3), (4, 3), (8, 3), (4, 2)])
+def test_karman_slabs_multi_step_passes_across_ranks(size, depth):
+    """Boundary-bearing lattices on N ranks take multi-step passes too (slabs with as many ghost rows that carry the
     neighbour's kinds; strip windows next to boundary rows and slab edges with ghost stores + flag handshake). With 4
     ranks the plate sits on the first row of rank 1, i.e. on rank 0's ghost rows; with 8 ranks rank 1 has boundary cells
     on its ghost rows ONLY. Must equal the single-block oracle."""
     place = _placement(size)
-    out = _torchrun('mp_karman_slabs.py', size, 29580 + size, *place)
-    assert f'OK {size} karman slabs' in out
+    out = _torchrun('mp_karman_slabs.py', size, 29580 + size + depth, '--depth', str(depth), *place)
+    assert f'OK {size} karman slabs, {depth} steps per pass' in out
 
 
 @pytest.mark.parametrize('size,depth', [(2, 3), (4, 3), (2, 2)])

@@ -671,10 +671,11 @@ def _karman_bundle(P, shape, second_plate=False):
     return bundle, d
 
 
+@pytest.mark.parametrize('depth', [2, 3])
 @pytest.mark.parametrize('shape,where,second', [((1024, 1024), 'clean', False), ((1024, 1024), 'plate', False),
                                                 ((2050, 512), 'outlet', False), ((2050, 512), 'inlet', True),
                                                 ((1024, 1024), 'next_to_strip', True)])
-def test_two_steps_per_pass_with_boundary_cells(P, oracle, shape, where, second):
+def test_two_steps_per_pass_with_boundary_cells(P, oracle, shape, where, second, depth):
     """Lattices WITH boundary cells take two steps per pass too: k_step2x on the rows whose two-step cone is all
     fluid, two one-step mask launches through a window on each strip of other rows (plan_strips). Must equal
     one-step launches and the C oracle bit for bit, probe ring included, wherever the probe sits."""
@@ -685,6 +686,7 @@ def test_two_steps_per_pass_with_boundary_cells(P, oracle, shape, where, second)
     px, py = {'clean': (nx // 2, ny // 3), 'plate': (nx // 4 + 1, ny // 2), 'outlet': (nx - 2, 5), 'inlet': (1, ny - 1),
               'next_to_strip': (nx // 4 - 3, ny // 2 + 1)}[where]
     fused = Lattice(nx, ny, bundle.kind_map(shape))
+    fused.set_option('fused_depth', depth)
     plain = Lattice(nx, ny, bundle.kind_map(shape))
     plain.set_option('fused', 0)
     for lat in (fused, plain):
@@ -695,13 +697,16 @@ def test_two_steps_per_pass_with_boundary_cells(P, oracle, shape, where, second)
         fused.run(n)
         plain.run(n)
     strips = 3 if second else 2          # {outlet rows, inlet row} wrap into one strip; one strip per plate
-    per_pass = 1 + 2 * strips            # k_step2x over the clean ranges (two per launch) + two launches per strip
-    if second:
-        per_pass += 1                    # three clean ranges -> two k_step2x launches
+    clean = 2 if second else 1           # launches of the multi-step kernel over the clean ranges (two ranges per launch)
     assert plain.launches - p0 == 2 * 18
-    # 7 = 3 passes + a one-step launch (mask-free kernel + edge list), 1, 8 = 4 passes, 2 = 1 pass: calls may END on a pass
-    # (results are then materialised from the strip windows and by re-running the clean rows in FINAL mode)
-    assert fused.launches - l0 == (3 * per_pass + 2) + 2 + 4 * per_pass + per_pass, 'the two-step pass was not used'
+    # a pass of d steps = the multi-step kernel over the clean ranges + d mask launches per strip; a one-step launch = mask-free
+    # kernel + edge list. Calls may END on a pass (results: strip windows + FINAL re-run of the clean rows).
+    pp = lambda d: clean + d * strips
+    if depth == 2:                        # 7 = 2+2+2+1, 1, 8 = 2+2+2+2, 2
+        expect = (3 * pp(2) + 2) + 2 + 4 * pp(2) + pp(2)
+    else:                                 # 7 = 3+3+1, 1, 8 = 3+3+2, 2
+        expect = (2 * pp(3) + 2) + 2 + (2 * pp(3) + pp(2)) + pp(2)
+    assert fused.launches - l0 == expect, 'the multi-step pass was not used'
     for a, b, nm in zip(fused.fields(), plain.fields(), 'f rho u'.split()):
         assert_parity(a, b, f'{shape} {where} {nm}')
     assert_parity(fused.probe_read(1, 18), plain.probe_read(1, 18), 'probe ring')
