@@ -165,6 +165,17 @@ class FakeLib:
                 c.samples[c.t] = np.array(c.state[2][c.probe[0], c.probe[1]])
         return 0
 
+    def lbm_run_host(self, ctx, f, rho, u, omega, n, fo, ro, uo):
+        c = self._c(ctx)
+        rc = self.lbm_upload(ctx, f, rho, u, omega) or self.lbm_step(ctx, omega, n)
+        if rc:
+            return rc
+        c.calls.append(('run_host', n))
+        for ptr, src, tail in ((fo, c.state[0], (9,)), (ro, c.state[1], ()), (uo, c.state[2], (2,))):
+            if ptr:
+                _arr(ptr, (c.nx, c.ny) + tail)[...] = src
+        return 0
+
     def lbm_materialize_region(self, ctx, x0, x1, y0, y1, f, rho, u):
         c = self._c(ctx)
         if c.t == 0:

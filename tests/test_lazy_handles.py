@@ -331,3 +331,23 @@ def test_out_of_device_memory_retires_idle_lattices_and_retries(L):
         g = L.lattice_boltzmann_step(*start((n, 10), seed=n), 1.0)
         assert np.array_equal(np.asarray(g[1]), _run_ref((n, 10), n, 1)[1])
     assert len(L.fake.ctxs) <= 2
+
+
+def test_run_host_is_load_run_fields_and_keeps_handles_valid(L):
+    """Lattice.run_host (lbm_run_host: the whole job from and to host arrays in one call) must leave results handed out
+    earlier readable and restart the lattice's clock like a load."""
+    from lattice_boltzmann_parallel_solver_b200.engine import Lattice
+    f, rho, u = start(seed=21)
+    lat = Lattice(12, 10)
+    lat.load(f, rho, u, 1.0)
+    old = lat.request_step(1.0)                          # a queued step whose result somebody still holds
+    g = start(seed=22)
+    out = lat.run_host(*g, 1.3, 5, out=(g[0].copy(), None, g[2].copy()))
+    ref = g
+    for _ in range(5):
+        ref = onp.step(*ref, 1.3)
+    assert np.array_equal(out[0], ref[0]) and out[1] is None and np.array_equal(out[2], ref[2])
+    assert lat.time == 5 and lat._pending_n == 0
+    assert np.array_equal(np.asarray(old[1]), onp.step(f, rho, u, 1.0)[1])      # preserved before the lattice was reloaded
+    nxt = lat.request_step(1.3)                          # ... and the lattice goes on from the state run_host left
+    assert np.array_equal(np.asarray(nxt[2]), onp.step(*ref, 1.3)[2])
