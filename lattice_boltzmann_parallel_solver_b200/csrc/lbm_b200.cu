@@ -210,7 +210,7 @@ static deep_fn deep_kernel(int depth, bool halo, bool probe, bool final)
 {
     return depth == 2 ? deep_kernel_d<2>(halo, probe, final) : (depth == 3 ? deep_kernel_d<3>(halo, probe, final) : deep_kernel_d<4>(halo, probe, final));
 }
-static int deep_smem(int depth) { return (depth - 1) * (LBM_RING_ALL9 ? 27 : 18) * 2 * kDeepThreads * (int)sizeof(double); }
+static int deep_smem(int depth) { return (depth - 1) * 18 * 2 * kDeepThreads * (int)sizeof(double); }
 static int deep_width(int depth) { return 2 * kDeepThreads - 4 * (depth - 1); }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -1064,7 +1064,7 @@ static int pick_seg(const lbm_ctx *c, int rows, int depth = 2)
     int seg = 256;
     while (seg > 8 && strips * ((rows + seg - 1) / seg) < 2000) seg /= 2;
     if (seg < 128 || !c->wave_seg) return seg;
-    const long long slots = (long long)c->n_sm * (deep ? (depth == 2 ? 3 : (depth == 3 ? LBM_D3_MINB : 2)) : 4);
+    const long long slots = (long long)c->n_sm * (deep ? (depth == 2 ? 3 : 2) : 4);
     double best_eff = 0;
     int best = seg;
     for (int ns = (rows + 511) / 512; ns <= (rows + 127) / 128; ns++) {      // segments of 128 .. 512 rows

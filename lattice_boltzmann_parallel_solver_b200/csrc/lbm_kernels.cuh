@@ -720,24 +720,12 @@ __global__ void __launch_bounds__(T, 4) k_step2x(const __grid_constant__ StepPar
 // FINAL: the last level stops after the moments and writes reference-layout f_post / rho / u of time t+D — how results
 // are materialised after a call that ended on a multi-step pass (the other buffer still holds S_t).
 // -------------------------------------------------------------------------------------------------------
-#ifndef LBM_MERGE_LEVELS
-#define LBM_MERGE_LEVELS 1   // levels 2..D of an iteration in one basic block (instruction-level parallelism over 2(D-1) cells)
-#endif
-#ifndef LBM_RING_ALL9
-#define LBM_RING_ALL9 0   // the unshifted populations (0, 1, 3) travel through the rings too instead of held registers
-#endif
-#ifndef LBM_LATE_LOAD
-#define LBM_LATE_LOAD 1
-#endif
-#ifndef LBM_D3_MINB
-#define LBM_D3_MINB 2   // resident blocks per SM the three-step kernel is compiled for (register cap 255)
-#endif
 template <int T, int D>
 struct Deep {
     static constexpr int W = 2 * T - 4 * (D - 1);   // output columns per block
     static constexpr int RS = 2 * T;                // doubles per ring row
-    static constexpr int SP = LBM_RING_ALL9 ? 27 : 18;   // slot-populations per ring
-    static constexpr int MINB = D == 2 ? 3 : (D == 3 ? LBM_D3_MINB : 2);
+    static constexpr int SP = 18;                   // slot-populations per ring
+    static constexpr int MINB = D == 2 ? 3 : 2;     // resident blocks per SM the kernel is compiled for (D >= 3: 255 registers)
     static constexpr int SMEM = (D - 1) * SP * RS * (int)sizeof(double);
 };
 
@@ -748,9 +736,7 @@ __global__ void __launch_bounds__(T, Deep<T, D>::MINB) k_stepNx(const __grid_con
     static_assert(D >= 2 && D <= 4, "depth");
     if (HALO && !halo_wait(P)) return;
     constexpr int W = Deep<T, D>::W, RS = Deep<T, D>::RS, SP = Deep<T, D>::SP;
-    constexpr bool MERGE = LBM_MERGE_LEVELS != 0;
-    constexpr bool LATE_LOAD = LBM_LATE_LOAD != 0 && D >= 3;
-    constexpr bool ALL9 = LBM_RING_ALL9 != 0;
+    constexpr bool LATE_LOAD = D >= 3;   // the next row's loads are issued before the LAST level of phase B only
     const int tid = threadIdx.x;
     const int y0 = (blockIdx.x + P.strip0) * W;
     int x0, x1;
@@ -820,12 +806,6 @@ __global__ void __launch_bounds__(T, Deep<T, D>::MINB) k_stepNx(const __grid_con
         R[(10 + q4) * RS] = sa[8];  R[(10 + q4) * RS + T] = sb[8];
         R[(14 + q2) * RS] = sa[6];  R[(14 + q2) * RS + T] = sb[6];
         R[(16 + q2) * RS] = sa[7];  R[(16 + q2) * RS + T] = sb[7];
-        if (ALL9) {   // own pair only, never shifted: one 128-bit word per population (3: 2 slots, 0: 3 slots, 1: 4 slots)
-            double2 *O = reinterpret_cast<double2 *>(ring + (size_t)b * SP * RS) + tid;
-            O[(18 + q2) * T] = make_double2(sa[3], sb[3]);
-            O[(20 + q3) * T] = make_double2(sa[0], sb[0]);
-            O[(23 + q4) * T] = make_double2(sa[1], sb[1]);
-        }
     };
     // the six y-moving pulls of the pair on intermediate row q: 5, 8 from row q-1; 2, 4 from row q; 6, 7 from row q+1.
     // Even cell (column 2t): c_y = +1 pulls the odd column of pair t-1, c_y = -1 the odd column of pair t;
@@ -839,13 +819,6 @@ __global__ void __launch_bounds__(T, Deep<T, D>::MINB) k_stepNx(const __grid_con
         ha[8] = R[(10 + a4) * RS + T + tid]; hb[8] = R[(10 + a4) * RS + tp];
         ha[6] = R[(14 + d2) * RS + T + tm];  hb[6] = R[(14 + d2) * RS + tid];
         ha[7] = R[(16 + d2) * RS + T + tid]; hb[7] = R[(16 + d2) * RS + tp];
-        if (ALL9) {   // 3 from row q+1, 0 from row q, 1 from row q-1
-            const double2 *O = reinterpret_cast<const double2 *>(R) + tid;
-            const double2 v3 = O[(18 + d2) * T], v0 = O[(20 + m3) * T], v1 = O[(23 + a4) * T];
-            ha[3] = v3.x; hb[3] = v3.y;
-            ha[0] = v0.x; hb[0] = v0.y;
-            ha[1] = v1.x; hb[1] = v1.y;
-        }
     };
 
     // unshifted populations in flight between the levels (a = even column, b = odd column of the pair):
@@ -886,7 +859,6 @@ __global__ void __launch_bounds__(T, Deep<T, D>::MINB) k_stepNx(const __grid_con
         bool slow = false, sl_a[D + 1] = {}, sl_b[D + 1] = {};
         auto gather_level = [&](int d, double (&ha)[9], double (&hb)[9]) {
             ring_gather(d - 2, q - (unsigned)(2 * d - 3), ha, hb);
-            if (ALL9) return;
             if (d == 2) {
                 ha[0] = g0a;    hb[0] = g0b;
                 ha[1] = g1a[1]; hb[1] = g1b[1];
@@ -945,7 +917,7 @@ __global__ void __launch_bounds__(T, Deep<T, D>::MINB) k_stepNx(const __grid_con
                     }
                 }
             }
-            if (!ALL9 && d < D) {   // hand the unshifted populations of the row just written to level d+1
+            if (d < D) {   // hand the unshifted populations of the row just written to level d+1
                 k1a[d - 1][2] = k1a[d - 1][1]; k1a[d - 1][1] = k1a[d - 1][0]; k1a[d - 1][0] = ta[d][1];
                 k1b[d - 1][2] = k1b[d - 1][1]; k1b[d - 1][1] = k1b[d - 1][0]; k1b[d - 1][0] = tb[d][1];
                 k0a[d - 1][1] = k0a[d - 1][0]; k0a[d - 1][0] = ta[d][0];
@@ -974,23 +946,16 @@ __global__ void __launch_bounds__(T, Deep<T, D>::MINB) k_stepNx(const __grid_con
                     fin_b[i] = hb[i];
                 }
             }
-            if (!MERGE) {   // one basic block per level
-                if (sl_a[d] | sl_b[d]) redo_level(d);
-                store_level(d);
-            }
         }
-        if (MERGE) {        // all levels of phase B in one basic block: more instruction-level parallelism, more registers
-            if (slow) {
+        // all levels of phase B form one basic block up to here (four cells in flight for D = 3); the cold redo and the stores follow
+        if (slow) {
 #pragma unroll
-                for (int d = D; d >= 2; d--) redo_level(d);
-            }
+            for (int d = D; d >= 2; d--) redo_level(d);
+        }
 #pragma unroll
-            for (int d = D; d >= 2; d--) store_level(d);
-        }
-        if (!ALL9) {
-            g1a[1] = g1a[0]; g1a[0] = sa[1]; g0a = sa[0];
-            g1b[1] = g1b[0]; g1b[0] = sb[1]; g0b = sb[0];
-        }
+        for (int d = D; d >= 2; d--) store_level(d);
+        g1a[1] = g1a[0]; g1a[0] = sa[1]; g0a = sa[0];
+        g1b[1] = g1b[0]; g1b[0] = sb[1]; g0b = sb[0];
     }
     if (HALO) halo_signal(P);
 }
@@ -1436,7 +1401,7 @@ __global__ void k_selftest_arith(long long n, unsigned long long seed, unsigned 
         if (!same && atomicAdd(out + 1, 1ULL) == 0) out[4] = (unsigned long long)__double_as_longlong(a);
     }
     // the branch-free variants of the multi-step kernels: whatever they do not flag as `slow` must be the IEEE result
-    if (is_pos_normal(b)) {
+    if (b != 0.0) {
         bool slow = false;
         const double mine = div_fast(a, b, rcp_refined(b), slow), ref = __ddiv_rn(a, b);
         const bool same = __double_as_longlong(mine) == __double_as_longlong(ref) || (mine != mine && ref != ref);
