@@ -209,6 +209,15 @@ int lbm_materialize(lbm_ctx *ctx, double *f, double *rho, double *u);
 /* Same for the sub-rectangle [x0,x1) x [y0,y1) (row-major, packed). */
 int lbm_materialize_region(lbm_ctx *ctx, int x0, int x1, int y0, int y1, double *f, double *rho, double *u);
 
+/* Device-side history for drivers that keep a field of EVERY step and look at a few of them after the loop
+ * (velocities.append(velocity), src/experiments.py:254, :542): lbm_history_config allocates n_slots slots of
+ * (density, velocity) on the device (0 frees them); lbm_history_store parks the fields of the current time in a slot —
+ * one asynchronous launch, no copy, no synchronisation; lbm_history_read brings a slot to the host (either pointer may be
+ * NULL; synchronous). */
+int lbm_history_config(lbm_ctx *ctx, int n_slots);
+int lbm_history_store(lbm_ctx *ctx, int slot);
+int lbm_history_read(lbm_ctx *ctx, int slot, double *rho, double *u);
+
 /* Probe: records (u_x, u_y) at one cell after every step (experiments.py:703-704) into a ring in host-mapped
  * memory — the cell's thread stores the sample, a system-scope fence and the step number straight to the host as
  * the step completes. lbm_probe_read copies the samples of steps [t0, t0+n) — at most `capacity` behind

@@ -89,6 +89,9 @@ SIGNATURES = {
     'lbm_probe_config': (C.c_int, [_CTX, C.c_int, C.c_int, C.c_int]),
     'lbm_probe_read': (C.c_int, [_CTX, C.c_int64, C.c_int, _DP]),
     'lbm_minmax': (C.c_int, [_CTX, C.c_int, C.c_int, C.c_int, C.c_int, _DP]),
+    'lbm_history_config': (C.c_int, [_CTX, C.c_int]),
+    'lbm_history_store': (C.c_int, [_CTX, C.c_int]),
+    'lbm_history_read': (C.c_int, [_CTX, C.c_int, _DP, _DP]),
     'lbm_halo_export_handle': (C.c_int, [_CTX, C.POINTER(HaloExport)]),
     'lbm_halo_connect': (C.c_int, [_CTX, C.c_int, C.POINTER(HaloExport)]),
     'lbm_halo_finalize': (C.c_int, [_CTX]),

@@ -170,6 +170,9 @@ struct lbm_ctx {
     bool halo_ready = false, any_remote = false;
     cudaStream_t stream = nullptr, stream_edge = nullptr;
     cudaEvent_t ev_main = nullptr, ev_edge = nullptr;
+    // device-side history of (rho, u) fields (lbm_history_*): n_hist slots of 3 * NX * NY doubles
+    double *hist = nullptr;
+    int n_hist = 0;
     // lbm_run_host: double-buffered staging (set 0 of the inputs is stage_f / stage_rho / stage_u), copy streams, events
     struct Streamed {
         double *in_f[2] = {}, *in_rho[2] = {}, *in_u[2] = {}, *out_f[2] = {}, *out_rho[2] = {}, *out_u[2] = {};
@@ -452,6 +455,7 @@ extern "C" int lbm_destroy(lbm_ctx *c)
                     c->done_counter, c->err_flag, c->stage_f, c->stage_rho, c->stage_u, c->mm_acc, c->tcount};
     for (void *b : bufs)
         if (b) cudaFree(b);
+    if (c->hist) cudaFree(c->hist);
     if (c->probe) cudaFreeHost(c->probe);
     if (c->progress) cudaFreeHost(c->progress);
     if (c->err_host) cudaFreeHost(c->err_host);
@@ -1623,7 +1627,10 @@ extern "C" int lbm_sync(lbm_ctx *c)
 }
 
 // f_post / rho / u of time t are stream+BC+moments of S_{t-1}, which the A/B scheme still holds in S[cur^1].
-static int materialize_rows(lbm_ctx *c, int x0, int x1, int y0, int y1, double *f, double *rho, double *u, bool to_host)
+// to_host: copy to the host pointers; else either reduce (min/max) or, with dev_rho / dev_u set, write the packed fields
+// straight into device memory (history slots) without any copy or synchronisation
+static int materialize_rows(lbm_ctx *c, int x0, int x1, int y0, int y1, double *f, double *rho, double *u, bool to_host,
+                            double *dev_rho = nullptr, double *dev_u = nullptr)
 {
     StepParams P;
     fill_common(c, P, c->cur ^ 1, c->cur, c->omega);
@@ -1644,6 +1651,11 @@ static int materialize_rows(lbm_ctx *c, int x0, int x1, int y0, int y1, double *
         P.o_f = f ? c->stage_f : nullptr;
         P.o_rho = rho || !to_host ? c->stage_rho : nullptr;
         P.o_u = u || !to_host ? c->stage_u : nullptr;
+        if (dev_rho || dev_u) {
+            P.o_f = nullptr;
+            P.o_rho = dev_rho ? dev_rho + (size_t)(xa - x0) * w : nullptr;
+            P.o_u = dev_u ? dev_u + (size_t)(xa - x0) * w * 2 : nullptr;
+        }
         const int blocks = nr * P.bpr;
         cudaError_t e = cudaSuccess;
         // the call ended on a multi-step pass: S[cur^1] is S_{t-d}. Re-run the pass over rows [lo, lo + n) with its last
@@ -1700,6 +1712,7 @@ static int materialize_rows(lbm_ctx *c, int x0, int x1, int y0, int y1, double *
         if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "materialize kernel launch failed: %s", cudaGetErrorString(e));
         c->launches++;
         const size_t n = (size_t)nr * w, o = (size_t)(xa - x0) * w;
+        if (dev_rho || dev_u) continue;   // device destination: nothing to copy, nothing to wait for
         if (to_host) {
             if (f) CK(cudaMemcpyAsync(f + o * 9, c->stage_f, n * 72, cudaMemcpyDeviceToHost, c->stream));
             if (rho) CK(cudaMemcpyAsync(rho + o, c->stage_rho, n * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -1713,6 +1726,7 @@ static int materialize_rows(lbm_ctx *c, int x0, int x1, int y0, int y1, double *
             CK(cudaStreamSynchronize(c->stream));
         }
     }
+    if (dev_rho || dev_u) return LBM_OK;
     return async_error(c, "lbm_materialize");
 }
 
@@ -1997,6 +2011,49 @@ extern "C" int lbm_run_host(lbm_ctx *c, const double *f, const double *rho, cons
     CK(cudaStreamSynchronize(R.d2h));
     CK(cudaStreamSynchronize(R.h2d));
     return async_error(c, "lbm_run_host");
+}
+
+// ---- device-side history -------------------------------------------------------------------------------------
+// Drivers that KEEP a field of every step (velocities.append(velocity), src/experiments.py:254, :542) and look at a few of
+// them after the loop: the fields of a step are parked in a device slot by one asynchronous launch instead of travelling
+// to the host behind a synchronisation after every step; a slot is read back only if somebody looks at it.
+extern "C" int lbm_history_config(lbm_ctx *c, int n_slots)
+{
+    if (!c || n_slots < 0) return fail(LBM_ERR_ARG, "lbm_history_config: bad argument");
+    if (c->gx >= 2) return fail(LBM_ERR_ARG, "lbm_history_config: slabs with ghost rows of the multi-step kernel keep no history");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->hist) CK(cudaFree(c->hist));
+    c->hist = nullptr;
+    c->n_hist = 0;
+    if (n_slots == 0) return LBM_OK;
+    const size_t bytes = (size_t)n_slots * 3 * c->NX * c->NY * 8;
+    if (cudaMalloc(&c->hist, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(LBM_ERR_NOMEM, "cannot allocate %.1f MB for %d history slots", bytes / 1e6, n_slots);
+    }
+    c->n_hist = n_slots;
+    return LBM_OK;
+}
+
+extern "C" int lbm_history_store(lbm_ctx *c, int slot)
+{
+    if (int rc = check_region(c, 0, c ? c->NX : 0, 0, c ? c->NY : 0, "lbm_history_store")) return rc;
+    if (slot < 0 || slot >= c->n_hist) return fail(LBM_ERR_ARG, "lbm_history_store: slot %d of %d", slot, c->n_hist);
+    double *base = c->hist + (size_t)slot * 3 * c->NX * c->NY;
+    return materialize_rows(c, 0, c->NX, 0, c->NY, nullptr, nullptr, nullptr, false, base, base + (size_t)c->NX * c->NY);
+}
+
+extern "C" int lbm_history_read(lbm_ctx *c, int slot, double *rho, double *u)
+{
+    if (!c || slot < 0 || slot >= c->n_hist) return fail(LBM_ERR_ARG, "lbm_history_read: bad slot");
+    CK(cudaSetDevice(c->device));
+    const size_t n = (size_t)c->NX * c->NY;
+    const double *base = c->hist + (size_t)slot * 3 * n;
+    if (rho) CK(cudaMemcpyAsync(rho, base, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (u) CK(cudaMemcpyAsync(u, base + n, n * 16, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return async_error(c, "lbm_history_read");
 }
 
 extern "C" int lbm_minmax(lbm_ctx *c, int x0, int x1, int y0, int y1, double out[4])

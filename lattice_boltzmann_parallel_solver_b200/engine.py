@@ -19,13 +19,22 @@ Drivers that look at ONE velocity cell after every step (`vel_at_p.append(np.lin
 experiments.py:703-704) cannot defer anything; for them the second consecutive read of the same cell configures the
 device-side probe on it (`Lattice._probe_sample`), after which a read costs one step launch and a 16-byte copy out
 of the host-mapped probe ring.
+
+Drivers that KEEP a field of every step and look at a few afterwards (`velocities.append(velocity)`,
+experiments.py:254, :542): when the device has to move past a time whose density / velocity handles are still
+referenced, those fields are parked in a device history slot by one asynchronous launch (`Lattice._park`,
+lbm_history_*) and only come to the host if somebody reads them; with no free slot (or when `f` itself is kept) they
+are materialised to the host as before.
 """
+import os
 import weakref
 
 import numpy as np
 
 from . import _native as N
 
+HISTORY_BYTES = int(os.environ.get('LBM_HISTORY_MB', '256')) << 20   # device memory for kept-but-unread (rho, u) fields
+HISTORY_MAX_SLOTS = 1024
 MAX_DEFERRED = 64   # steps queued by lattice_boltzmann_step before they are launched as one batch
 AUTO_PROBE_CAPACITY = 4096   # ring entries of the probe that velocity[px, py] reads configure by themselves
 
@@ -61,6 +70,9 @@ class Lattice:
         self._pending_n = 0           # how many of them
         self._generation = 0          # bumped by every load: handles of an earlier upload never count as current
         self._handles = {}            # api time -> list of weakrefs to LatticeArray
+        # device-side history (lbm_history_*): results that are kept but not looked at are parked on the device
+        self._hist_free = None        # free slot indices; None = not configured yet, [] may also mean "switched off"
+        self._parked = weakref.WeakSet()
 
     # ---- lifetime ----------------------------------------------------------------------------------------
     def retire(self):
@@ -73,6 +85,8 @@ class Lattice:
 
     def close(self):
         if self._ctx:
+            for slot in list(self._parked):   # results parked on the device must outlive it
+                slot.drain()
             self.lib.lbm_destroy(self._ctx)
             self._ctx = N._CTX()
 
@@ -236,14 +250,37 @@ class Lattice:
 
     def _preserve(self, t):
         """Materialise every still-referenced handle of device time t (must be the current device time)."""
-        live = [h for h in self._live(t) if h._value is None]
+        live = [h for h in self._live(t) if h._value is None and h._hist is None]
         if live and t == self.time and t > 0:
             want = {h._which for h in live}
+            if 'f' not in want and self._park(live):
+                self._handles.pop(t, None)
+                return
             f, rho, u = self.fields('f' in want, 'rho' in want, 'u' in want)
             for h in live:
                 h._value = {'f': f, 'rho': rho, 'u': u}[h._which]
                 h._value.setflags(write=False)
         self._handles.pop(t, None)
+
+    def _park(self, handles):
+        """Keep the density / velocity of the current time in a device history slot for these handles (one asynchronous
+        launch) instead of bringing them to the host now: the `velocities.append(velocity)` loops of the reference
+        (experiments.py:254, :542) look at a handful of the fields they keep. False when no slot is to be had."""
+        if self._hist_free is None:
+            self._hist_free = []
+            per_slot = self.nx * self.ny * 24
+            n = min(HISTORY_MAX_SLOTS, HISTORY_BYTES // per_slot)
+            if n >= 4 and self.ghost[0] < 2:
+                try:
+                    N.check(self.lib.lbm_history_config(self._ctx, int(n)))
+                    self._hist_free = list(range(int(n) - 1, -1, -1))
+                except MemoryError:
+                    pass
+        if not self._hist_free:
+            return False
+        slot = _HistorySlot(self, self._hist_free.pop(), handles)
+        N.check(self.lib.lbm_history_store(self._ctx, slot.index))
+        return True
 
     def flush(self, upto=None):
         """Launch the queued steps (all of them, or up to api time `upto`). Times whose handles are still
@@ -330,6 +367,40 @@ def run_blocks(blocks, n_steps, omega=None, chunk=None):
         done += n
 
 
+class _HistorySlot:
+    """One device history slot and the handles parked in it. The slot returns to the free list when the last of its
+    handles has been read or dropped."""
+
+    def __init__(self, lattice, index, handles):
+        self.lattice, self.index = lattice, index
+        self.handles = [weakref.ref(h) for h in handles]
+        for h in handles:
+            h._hist = self
+        lattice._parked.add(self)
+
+    def read(self, which):
+        L = self.lattice
+        if not L._ctx:
+            raise RuntimeError('history slot of a closed lattice (internal error)')
+        out = np.empty(_SHAPES[which](L.nx, L.ny))
+        N.check(L.lib.lbm_history_read(L._ctx, self.index, N.dptr(out) if which == 'rho' else None,
+                                       N.dptr(out) if which == 'u' else None))
+        return out
+
+    def drain(self):
+        for r in self.handles:
+            h = r()
+            if h is not None and h._hist is self:
+                h.materialize()
+
+    def __del__(self):
+        try:
+            if self.lattice._ctx and self.lattice._hist_free is not None:
+                self.lattice._hist_free.append(self.index)
+        except Exception:
+            pass
+
+
 _SHAPES = {'f': lambda nx, ny: (nx, ny, 9), 'rho': lambda nx, ny: (nx, ny), 'u': lambda nx, ny: (nx, ny, 2)}
 
 
@@ -347,6 +418,7 @@ class LatticeArray(np.lib.mixins.NDArrayOperatorsMixin):
         self._lattice, self._t, self._which = lattice, t, which
         self._generation = lattice._generation
         self._value = None
+        self._hist = None             # _HistorySlot while the field is parked on the device
         self._dirty = False           # written through __setitem__: the device copy no longer matches
         self.shape = _SHAPES[which](lattice.nx, lattice.ny)
         self.dtype = np.dtype(np.float64)
@@ -363,7 +435,16 @@ class LatticeArray(np.lib.mixins.NDArrayOperatorsMixin):
                 raise RuntimeError('stale LatticeArray: the lattice advanced without this handle being preserved '
                                    '(internal error)')
 
+    @property
+    def _on_device(self):
+        """Not on the host and not parked: the field is (or will be) the lattice's current state."""
+        return self._value is None and self._hist is None
+
     def materialize(self):
+        if self._value is None and self._hist is not None:
+            self._value = self._hist.read(self._which)
+            self._value.setflags(write=False)
+            self._hist = None
         if self._value is None:
             self._bring_current()
             L = self._lattice
@@ -403,7 +484,7 @@ class LatticeArray(np.lib.mixins.NDArrayOperatorsMixin):
 
     def __array_function__(self, func, types, args, kwargs):
         if func in (np.amin, np.amax, np.min, np.max) and len(args) == 1 and not kwargs and args[0] is self \
-                and self._value is None and self._which in ('rho', 'u'):
+                and self._on_device and self._which in ('rho', 'u'):
             return self._extremum(func in (np.amax, np.max))
 
         def conv(x):
@@ -422,15 +503,15 @@ class LatticeArray(np.lib.mixins.NDArrayOperatorsMixin):
         return np.float64(mx_u if want_max else mn_u)
 
     def min(self, *a, **k):
-        return self._extremum(False) if not a and not k and self._value is None and self._which != 'f' else \
+        return self._extremum(False) if not a and not k and self._on_device and self._which != 'f' else \
             self.materialize().min(*a, **k)
 
     def max(self, *a, **k):
-        return self._extremum(True) if not a and not k and self._value is None and self._which != 'f' else \
+        return self._extremum(True) if not a and not k and self._on_device and self._which != 'f' else \
             self.materialize().max(*a, **k)
 
     def __getitem__(self, index):
-        if self._value is None and isinstance(index, tuple) and len(index) >= 2:
+        if self._on_device and isinstance(index, tuple) and len(index) >= 2:
             ix, iy = index[0], index[1]
             if isinstance(ix, (int, np.integer)) and isinstance(iy, (int, np.integer)):
                 # velocity[px, py, ...] every step (experiments.py:703-704): fetch one cell, not the lattice
@@ -463,5 +544,5 @@ class LatticeArray(np.lib.mixins.NDArrayOperatorsMixin):
         return getattr(self.materialize(), name)
 
     def __repr__(self):
-        state = 'host' if self._value is not None else 'device'
+        state = 'host' if self._value is not None else 'parked' if self._hist is not None else 'device'
         return f'LatticeArray({self._which}, t={self._t}, shape={self.shape}, {state})'

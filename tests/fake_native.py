@@ -29,6 +29,7 @@ class _Ctx:
         self.calls = []          # ('step', n) / ('fields', 1) / ('probe_config', x, y) / ('probe_read', t0, n) in call order
         self.probe = None        # (x, y, capacity, t_config)
         self.samples = {}        # t -> (ux, uy)
+        self.hist = []           # history slots: None or (rho, u)
 
 
 class FakeLib:
@@ -201,6 +202,37 @@ class FakeLib:
             return 1
         c.calls.append(('probe_read', t0, n))
         _arr(out, (n, 2))[...] = [c.samples[t] for t in range(t0, t0 + n)]
+        return 0
+
+    def lbm_history_config(self, ctx, n_slots):
+        c = self._c(ctx)
+        if c.ghost[0] >= 2:
+            self.err = b'lbm_history_config: slabs keep no history'
+            return 1
+        c.hist = [None] * n_slots
+        c.calls.append(('hist_config', n_slots))
+        return 0
+
+    def lbm_history_store(self, ctx, slot):
+        c = self._c(ctx)
+        if c.t == 0 or not 0 <= slot < len(c.hist):
+            self.err = b'lbm_history_store: bad slot or no step taken'
+            return 1
+        c.hist[slot] = (c.state[1].copy(), c.state[2].copy())
+        c.launches += 1
+        c.calls.append(('hist_store', slot))
+        return 0
+
+    def lbm_history_read(self, ctx, slot, rho, u):
+        c = self._c(ctx)
+        if not 0 <= slot < len(c.hist) or c.hist[slot] is None:
+            self.err = b'lbm_history_read: bad slot'
+            return 1
+        c.calls.append(('hist_read', slot))
+        if rho:
+            _arr(rho, (c.nx, c.ny))[...] = c.hist[slot][0]
+        if u:
+            _arr(u, (c.nx, c.ny, 2))[...] = c.hist[slot][1]
         return 0
 
     def lbm_minmax(self, ctx, x0, x1, y0, y1, out):

@@ -84,6 +84,20 @@ def main():
         E.plot_evolution_of_velocity(lattice_grid_shape=(20, 16), epsilon=0.05, omega=1.2, time_steps=100, number_of_visualizations=10)
         lines = [a for a in plotted('plt.subplots()[') if len(a) >= 2 and np.ndim(a[1]) == 1 and len(a[1]) == 16]
         res['evolution_lines'] = np.array([np.asarray(a[1], dtype=float) for a in lines])
+        # (7), (8) Couette / Poiseuille evolution: velocities.append(velocity) after EVERY step, a few of them plotted after
+        #     the loop (:225-301, :503-583) -- kept results are parked in the device history, not copied out per step
+        for tag, call, ly in (('couette_evolution', lambda: E.plot_couette_flow_evolution(
+                                  lattice_grid_shape=(14, 12), omega=1.1, U=0.04, time_steps=90, number_of_visualizations=10), 12),
+                              ('poiseuille_evolution', lambda: E.plot_poiseuille_flow_evolution(
+                                  lattice_grid_shape=(18, 10), omega=1.4, delta_p=0.002, time_steps=90, number_of_visualizations=10), 10)):
+            if mode == 'fake' and tag == 'poiseuille_evolution':
+                continue                                        # the fake library has no pressure-periodic boundary
+            matplotlib.calls.clear()
+            call()
+            sim = [a for name, a, k in matplotlib.calls if name.endswith('.plot') and k.get('linestyle') == ':']
+            assert len(sim) == 10, len(sim)
+            res[tag] = np.array([np.asarray(a[0], dtype=float) for a in sim])
+            assert res[tag].shape == (10, ly)
     # (6) main.py end to end (argparse -> experiments): couette_vectors with explicit sizes
     matplotlib.calls.clear()
     sys.argv = ['main.py', '-f', 'couette_vectors', '-l', '10', '12', '-t', '60', '-mwv', '0.03']

@@ -844,6 +844,60 @@ def test_streamed_run_from_and_to_host_memory(P, oracle, steps, chunk, depth):
     plain.close()
 
 
+@pytest.mark.parametrize('case', ['periodic_300x200', 'couette_100x100', 'karman_420x180', 'periodic_2048x1500'])
+def test_kept_results_are_parked_in_the_device_history(P, oracle, case):
+    """velocities.append(velocity) after every step (experiments.py:254, :542): kept density / velocity handles go to the
+    device history (one asynchronous launch each, lbm_history_*), come back bit-exact when read — in any order, also after
+    the lattice has been loaded again — and the last lattice is too large for slots (host materialisation instead)."""
+    L, BU = P.lattice_boltzmann_method, P.boundary_utils
+    from lattice_boltzmann_parallel_solver_b200 import engine
+    name, dims = case.split('_')
+    shape = tuple(int(v) for v in dims.split('x'))
+    steps = 7 if shape[0] > 1000 else 40
+    f, rho, u = random_state(oracle, shape, 11)
+    if name == 'periodic':
+        bundle, scen, omega = None, oracle.c.periodic(), 1.3
+    elif name == 'couette':
+        bundle, scen, omega = BU.couette_flow_boundary_conditions(*shape, 0.05, 1.0), oracle.c.couette(0.05, 1.0), 1.0
+    else:
+        import lattice_boltzmann_parallel_solver_b200 as pkg
+        B = pkg.boundary_conditions
+        plate = np.zeros(shape, dtype=bool); plate[shape[0] // 4, 70:110] = True
+        bundle = BU.BoundaryBundle('von_karman_serial', shape)
+        bundle.add(B.inlet(shape, 1.0, 0.1)).add(B.outlet()).add(B.rigid_object(plate))
+        scen, omega = oracle.c.karman(shape[0], shape[1], 1.0, 0.1, 40, ghost=0), 1.6
+    want, state = [], (f, rho, u)
+    for _ in range(steps):
+        state = oracle.c.run(*state, omega, scen, 1)
+        want.append(state)
+    kept_u, kept_rho = [], []
+    for t in range(steps):
+        f, rho, u = L.lattice_boltzmann_step(f, rho, u, omega, bundle)
+        kept_u.append(u)
+        if t % 3 == 0:
+            kept_rho.append(rho)
+    assert np.array_equal(np.asarray(f), want[-1][0])
+    lat = kept_u[0]._lattice
+    parked = [h for h in kept_u[:-1] if h._hist is not None]
+    if shape[0] > 1000:
+        assert not parked and lat._hist_free == []                   # 74 MB per slot: under four slots, history off
+    else:
+        assert len(parked) == steps - 1 and len(lat._hist_free) == min(engine.HISTORY_MAX_SLOTS, engine.HISTORY_BYTES // (shape[0] * shape[1] * 24)) - (steps - 1)
+    order = np.random.default_rng(3).permutation(steps)
+    for t in order[:steps // 2]:
+        assert np.array_equal(np.asarray(kept_u[t]), want[t][2]), t
+    # a fresh upload on the same lattice: parked results stay readable
+    f2, rho2, u2 = L.lattice_boltzmann_step(*random_state(oracle, shape, 12), omega, bundle)
+    np.asarray(rho2)
+    assert kept_u[0]._lattice is rho2._lattice
+    for t in order[steps // 2:]:
+        assert np.array_equal(np.asarray(kept_u[t]), want[t][2]), t
+    for i, h in enumerate(kept_rho):
+        assert np.array_equal(np.asarray(h), want[3 * i][1]), i
+    L.release_lattices()                                             # parked-but-unread handles survive the lattice
+    assert all(h._value is not None for h in kept_u + kept_rho)
+
+
 def test_options_and_state_errors(P, oracle):
     from lattice_boltzmann_parallel_solver_b200 import _native as N
     from lattice_boltzmann_parallel_solver_b200.engine import Lattice

@@ -351,3 +351,58 @@ def test_run_host_is_load_run_fields_and_keeps_handles_valid(L):
     assert np.array_equal(np.asarray(old[1]), onp.step(f, rho, u, 1.0)[1])      # preserved before the lattice was reloaded
     nxt = lat.request_step(1.3)                          # ... and the lattice goes on from the state run_host left
     assert np.array_equal(np.asarray(nxt[2]), onp.step(*ref, 1.3)[2])
+
+
+def test_kept_velocities_are_parked_on_the_device(L):
+    """velocities.append(velocity) every step (experiments.py:254, :542): no host materialisation inside the loop; the
+    fields come out of the device history when (and only when) they are looked at, and slots are recycled."""
+    lib, P = L.fake, L
+    f, rho, u = start(seed=5)
+    rf, rr, ru = f, rho, u
+    want = []
+    kept, kept_rho = [], []
+    for i in range(20):
+        f, rho, u = P.lattice_boltzmann_step(f, rho, u, 1.1)
+        kept.append(u)
+        if i % 5 == 0:
+            kept_rho.append(rho)
+        rf, rr, ru = onp.step(rf, rr, ru, 1.1)
+        want.append((rr.copy(), ru.copy()))
+    c = next(iter(lib.ctxs.values()))
+    np.testing.assert_array_equal(np.asarray(u), want[-1][1])           # flushes the queue
+    assert ('fields', 1) not in c.calls[:-1], c.calls                    # nothing came to the host inside the loop
+    assert sum(1 for x in c.calls if x[0] == 'hist_store') == 19
+    assert 'parked' in repr(kept[3])
+    np.testing.assert_array_equal(kept[3], want[3][1])
+    np.testing.assert_array_equal(kept_rho[1], want[5][0])
+    np.testing.assert_array_equal(np.asarray(kept[5]), want[5][1])       # same slot, other field
+    assert sum(1 for x in c.calls if x[0] == 'hist_read') == 3
+    lat = kept[0]._lattice
+    n_free = len(lat._hist_free)
+    del kept[11:15]      # (the slot of step 10 is still held by its density handle)
+    import gc; gc.collect()
+    assert len(lat._hist_free) == n_free + 4                             # dropped handles give their slots back
+    # a new upload on the same lattice (other initial state) leaves parked results readable; closing drains them
+    np.testing.assert_array_equal(kept[7], want[7][1])
+    lat.retire()
+    for i, j in ((0, 0), (1, 1), (2, 2), (4, 4), (6, 6), (8, 8), (9, 9), (10, 10), (11, 15), (12, 16), (14, 18)):
+        np.testing.assert_array_equal(kept[i], want[j][1])
+
+
+def test_history_falls_back_to_the_host_without_slots(L, monkeypatch):
+    lib, P = L.fake, L
+    from lattice_boltzmann_parallel_solver_b200 import engine
+    monkeypatch.setattr(engine, 'HISTORY_MAX_SLOTS', 4)
+    f, rho, u = start((8, 8), seed=6)
+    rf, rr, ru = f, rho, u
+    kept, want = [], []
+    for i in range(9):
+        f, rho, u = P.lattice_boltzmann_step(f, rho, u, 0.9)
+        kept.append(u)
+        rf, rr, ru = onp.step(rf, rr, ru, 0.9)
+        want.append(ru.copy())
+    np.testing.assert_array_equal(kept[-1], want[-1])       # the device passes steps 1..8, all of them still referenced
+    c = next(iter(lib.ctxs.values()))
+    assert sum(1 for x in c.calls if x[0] == 'hist_store') == 4 and c.calls.count(('fields', 1)) == 5
+    for a, b in zip(kept, want):
+        np.testing.assert_array_equal(a, b)

@@ -77,3 +77,14 @@ bcp = P.boundary_utils.poiseuille_flow_boundary_conditions(40, 24, 0.3345, 0.332
 r3 = rng.uniform(0.9, 1.1, (40, 24)); u3 = rng.uniform(-0.05, 0.05, (40, 24, 2)); f3 = onp.equilibrium(r3, u3)
 l3 = Lattice(40, 24, bcp.kind_map((40, 24))); l3.load(f3, r3, u3, 1.5); l3.run(40)
 print('poiseuille', all(np.array_equal(a, b) for a, b in zip(l3.fields(), oc.run(f3, r3, u3, 1.5, oc.poiseuille(0.3345, 0.3321), 40))))
+# device history: kept velocity handles parked by the FINAL kernels writing straight into history slots
+L = P.lattice_boltzmann_method
+r6 = rng.uniform(0.9, 1.1, (300, 200)); u6 = rng.uniform(-0.05, 0.05, (300, 200, 2)); f6 = onp.equilibrium(r6, u6)
+want, st, kept = [], (f6, r6, u6), []
+a, b, c = f6, r6, u6
+for _ in range(9):
+    st = oc.run(*st, 1.2, oc.periodic(), 1); want.append(st[2])
+    a, b, c = L.lattice_boltzmann_step(a, b, c, 1.2); kept.append(c)
+np.asarray(a)
+print('history', sum(h._hist is not None for h in kept) == 8, all(np.array_equal(np.asarray(h), w) for h, w in zip(kept[::-1], want[::-1])))
+L.release_lattices()
