@@ -1358,8 +1358,7 @@ static void cluster_plan(lbm_ctx *c)
     const int force_c = getenv("LBM_CLUSTER_SIZE") ? atoi(getenv("LBM_CLUSTER_SIZE")) : 0;
     for (int C : {16, 8, 4, 2, 1}) {
         if (C > c->NX || (force_c && C != force_c) || (!force_c && C < 8)) continue;
-        const int R = (c->NX + C - 1) / C;
-        if ((C - 1) * R >= c->NX) continue;                 // every CTA must own at least one row
+        const int R = (c->NX + C - 1) / C;                  // most rows a CTA owns (balanced split, k_cluster_steps)
         const long long per = (long long)R * c->NY;
         const size_t smem = (size_t)2 * 9 * per * sizeof(double);
         if (per > 2048 || smem > 220 * 1024) continue;

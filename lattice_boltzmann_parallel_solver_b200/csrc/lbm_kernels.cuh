@@ -965,7 +965,7 @@ __global__ void __launch_bounds__(T, Deep<T, D>::MINB) k_stepNx(const __grid_con
 // -------------------------------------------------------------------------------------------------------
 // Launch-bound lattices (BASELINE.json configs 1-3: 5 000 - 10 000 cells, 2 500 - 40 000 steps per run): MANY time
 // steps in ONE launch of a single thread-block cluster. The whole lattice lives in the cluster's distributed shared
-// memory — CTA r owns rows [r R, (r+1) R) of both A/B buffers — a thread owns one cell (or two) for the whole launch,
+// memory — CTA r owns rows [r NX / C, (r+1) NX / C) of both A/B buffers — a thread owns one cell (or two) for the whole launch,
 // so its kind, its three source-row pointers (local or a neighbour CTA's shared memory) and its destination are
 // computed once; a step is nine shared-memory pulls, the common cell update, nine stores and one hardware cluster
 // barrier (~0.2 us) instead of a kernel boundary (~2 us inside a replayed graph). The last two states are written
@@ -982,23 +982,19 @@ struct ClusterParams {
     double *ob[2];     // outlet side buffers of the source / the other global buffer
 };
 
-template <int I>
-__device__ __forceinline__ double cluster_pull_rule(const StepParams &P, const lbm_kind &k, const double *pm, const double *p0,
-                                                    const double *pp, int plane, int y, int ym, int yp, const double *out_cur)
+// Shared-memory addresses inside the cluster's window (32 bits): one `mapa` per source row at kernel start, then a
+// population of ANY cell of the cluster is one `ld.shared::cluster.f64` — own CTA or a neighbour's.
+__device__ __forceinline__ unsigned dsmem_map(unsigned addr, unsigned rank)
 {
-    constexpr int cx[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1}, cy[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
-    constexpr int opp[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
-    const int r = k.rule[I], type = r & 7, row = r >> 3;
-    if (type == LBM_RULE_PULL) {
-        const double *src = cx[I] == 1 ? pm : (cx[I] == -1 ? pp : p0);
-        return src[I * plane + (cy[I] == 1 ? ym : (cy[I] == -1 ? yp : y))];
-    }
-    if (type == LBM_RULE_BOUNCE) {
-        const double v = p0[opp[I] * plane + y];
-        return row ? sub(v, P.ktab[row * 9 + opp[I]]) : v;
-    }
-    if (type == LBM_RULE_CONST) return P.ctab[row * 9 + I];
-    return __ldcg(out_cur + (I == 3 ? 0 : (I == 6 ? 1 : 2)) * P.pitch + y);
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ double dsmem_ld(unsigned addr)
+{
+    double v;
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
 }
 
 template <bool MASK, int M, int TMAX>
@@ -1006,13 +1002,20 @@ __global__ void __launch_bounds__(TMAX, 1) k_cluster_steps(const __grid_constant
 {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
-    extern __shared__ double sm[];   // [2 buffers][9][R][NY]
+    extern __shared__ double sm[];   // [2 buffers][9][most rows per CTA][NY]
     const StepParams &P = Q.S;
     const int rank = (int)cluster.block_rank(), C = (int)cluster.num_blocks();
-    const int R = Q.R, NY = P.NY, NX = P.NX, plane = Q.n_cells;
+    const int NY = P.NY, NX = P.NX, plane = Q.n_cells;
     const int bstride = 9 * plane;                 // doubles per buffer
-    const int row_lo = rank * R, nrows = max(0, min(R, NX - row_lo));
+    // balanced split: CTA r owns rows [r NX / C, (r+1) NX / C) — sizes differ by at most one row, so any NX >= C uses
+    // all C SMs (100 rows on 16 CTAs: 6 or 7 rows each)
+    auto lo = [&](int r) { return (int)(((long long)r * NX) / C); };
+    auto own = [&](int x) { return (int)(((long long)(x + 1) * C - 1) / NX); };
+    const int row_lo = lo(rank), nrows = lo(rank + 1) - row_lo;
     const int tid = threadIdx.x, T = blockDim.x;
+    constexpr int kcx[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1}, kcy[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
+    constexpr int kopp[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
+    constexpr int G = (M == 2 && TMAX <= 512) ? 2 : 1;
 
     // S_t of my rows: global -> buffer 0
     for (int q = tid; q < nrows * NY; q += T) {
@@ -1021,106 +1024,155 @@ __global__ void __launch_bounds__(TMAX, 1) k_cluster_steps(const __grid_constant
 #pragma unroll
         for (int i = 0; i < 9; i++) sm[i * plane + q] = __ldcg(g + i * P.plane);
     }
-    // my cell(s): everything that does not change from step to step
+    // my cell(s): everything that does not change from step to step. Where population i comes from is ONE address per
+    // population for every kind of cell (the streamed neighbour, the cell's own opposite population for a bounce-back
+    // rule, the cell itself where the value is replaced afterwards), so the nine loads of a step are the same straight
+    // code for fluid and boundary cells; a boundary cell then patches its populations (wall velocity term, inlet
+    // constant, outlet copy) in a short branch.
     bool act[M];
-    int cy_[M], cym[M], cyp[M], cq[M], cx_[M];
-    unsigned kind[M];
+    int cy_[M], cq[M], cx_[M];
+    unsigned kind[M], src[M][9], todo[M];   // todo: bit i = subtract the wall term, bit 9+i = inlet constant, bit 18+i = outlet copy
     lbm_kind kd[M];
-    const double *pm[M], *p0[M], *pp[M];
+    const unsigned sm0 = (unsigned)__cvta_generic_to_shared(sm);
 #pragma unroll
     for (int m = 0; m < M; m++) {
         const int q = tid + m * T;
         act[m] = q < nrows * NY;
         const int r = act[m] ? q / NY : 0, y = act[m] ? q - r * NY : 0, x = row_lo + r;
-        cq[m] = q;
+        cq[m] = act[m] ? q : 0;
         cx_[m] = x;
         cy_[m] = y;
-        cym[m] = y == 0 ? NY - 1 : y - 1;
-        cyp[m] = y == NY - 1 ? 0 : y + 1;
+        const int ym = y == 0 ? NY - 1 : y - 1, yp = y == NY - 1 ? 0 : y + 1;
         const int xm = x == 0 ? NX - 1 : x - 1, xp = x == NX - 1 ? 0 : x + 1;
-        p0[m] = sm + r * NY;
-        pm[m] = cluster.map_shared_rank(sm, xm / R) + (xm % R) * NY;
-        pp[m] = cluster.map_shared_rank(sm, xp / R) + (xp % R) * NY;
+        const int om = own(xm), op = own(xp);
+        const unsigned b0 = dsmem_map(sm0, rank) + 8u * (unsigned)(r * NY);
+        const unsigned bm = dsmem_map(sm0, om) + 8u * (unsigned)((xm - lo(om)) * NY);
+        const unsigned bp = dsmem_map(sm0, op) + 8u * (unsigned)((xp - lo(op)) * NY);
         kind[m] = 0;
+        todo[m] = 0;
         kd[m] = lbm_kind{};
         if (MASK && act[m]) {
             kind[m] = P.kind_map[(long long)x * P.pitch + y];
             if (kind[m]) kd[m] = P.kinds[kind[m]];
+        }
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            const unsigned row = kcx[i] == 1 ? bm : (kcx[i] == -1 ? bp : b0);
+            const int col = kcy[i] == 1 ? ym : (kcy[i] == -1 ? yp : y);
+            unsigned a = row + 8u * (unsigned)(i * plane + col);
+            if (MASK && kind[m]) {
+                const int type = kd[m].rule[i] & 7, trow = kd[m].rule[i] >> 3;
+                if (type == LBM_RULE_BOUNCE) {
+                    a = b0 + 8u * (unsigned)(kopp[i] * plane + y);
+                    if (trow) todo[m] |= 1u << i;
+                } else if (type != LBM_RULE_PULL) {
+                    a = b0 + 8u * (unsigned)(i * plane + y);
+                    todo[m] |= 1u << ((type == LBM_RULE_CONST ? 9 : 18) + i);
+                }
+            }
+            src[m][i] = a;
         }
     }
     const long long tc0 = P.probe ? *P.tc_in : 0;
     cluster.sync();
 
     for (int s = 0; s < Q.n_steps; s++) {
-        const int so = (s & 1) ? bstride : 0, dofs = (s & 1) ? 0 : bstride;
+        const unsigned so = (s & 1) ? 8u * (unsigned)bstride : 0u;
+        const int dofs = (s & 1) ? 0 : bstride;
+        // two cells of a thread are interleaved (G = 2) where the block's register budget allows it (<= 512 threads: 128
+        // registers), else they are updated one after the other
 #pragma unroll
-        for (int m = 0; m < M; m++) {
-            if (!act[m]) continue;
-            const int y = cy_[m], ym = cym[m], yp = cyp[m];
-            const double *a = pm[m] + so, *b = p0[m] + so, *d = pp[m] + so;
-            double f[9];
-            if (MASK && kind[m]) {
-                const double *oc = Q.ob[s & 1];
-                f[0] = cluster_pull_rule<0>(P, kd[m], a, b, d, plane, y, ym, yp, oc);
-                f[1] = cluster_pull_rule<1>(P, kd[m], a, b, d, plane, y, ym, yp, oc);
-                f[2] = cluster_pull_rule<2>(P, kd[m], a, b, d, plane, y, ym, yp, oc);
-                f[3] = cluster_pull_rule<3>(P, kd[m], a, b, d, plane, y, ym, yp, oc);
-                f[4] = cluster_pull_rule<4>(P, kd[m], a, b, d, plane, y, ym, yp, oc);
-                f[5] = cluster_pull_rule<5>(P, kd[m], a, b, d, plane, y, ym, yp, oc);
-                f[6] = cluster_pull_rule<6>(P, kd[m], a, b, d, plane, y, ym, yp, oc);
-                f[7] = cluster_pull_rule<7>(P, kd[m], a, b, d, plane, y, ym, yp, oc);
-                f[8] = cluster_pull_rule<8>(P, kd[m], a, b, d, plane, y, ym, yp, oc);
-            } else {
-                f[0] = b[y];
-                f[1] = a[1 * plane + y];
-                f[2] = b[2 * plane + ym];
-                f[3] = d[3 * plane + y];
-                f[4] = b[4 * plane + yp];
-                f[5] = a[5 * plane + ym];
-                f[6] = d[6 * plane + ym];
-                f[7] = d[7 * plane + yp];
-                f[8] = a[8 * plane + yp];
-            }
-            double rho, ux, uy, p[9], e[9], o[9];
-            moments(f, rho, ux, uy);
-            if (P.probe && cx_[m] == P.px && y == P.py) {
-                const long long t_new = tc0 + s + 1;
-                double *slot = P.probe + 2 * (t_new % P.probe_cap);
-                slot[0] = ux;
-                slot[1] = uy;
-                publish_progress(P, t_new);
-            }
-            eq_poly(ux, uy, p);
-            eq_from_poly(rho, p, e);
-            collide(f, e, P.omega, o);
-            const unsigned flags = MASK ? kd[m].flags : 0u, skip = MASK ? kd[m].skip_store : 0u;
-            if (MASK && (flags & LBM_CELL_OUTLET_SRC)) {
-                double *on = Q.ob[(s + 1) & 1];
-                __stcg(on + 0 * P.pitch + y, f[3]);
-                __stcg(on + 1 * P.pitch + y, f[6]);
-                __stcg(on + 2 * P.pitch + y, f[7]);
-                __threadfence();
-            }
-            double *w = sm + dofs + cq[m];
+        for (int g = 0; g < M; g += G) {
+            double f[M][9];
 #pragma unroll
-            for (int i = 0; i < 9; i++)
-                if (!MASK || !((skip >> i) & 1)) w[i * plane] = o[i];
-            if (MASK && (flags & (LBM_CELL_PBC_IN_SRC | LBM_CELL_PBC_OUT_SRC))) {
-                // periodic_with_pressure_variations (boundary_conditions.py:337-344), see store_pbc: the virtual rows 0 and
-                // NX-1 belong to the first / last CTA of the cluster
-                if (flags & LBM_CELL_PBC_IN_SRC) {
-                    const double w1 = mul(LBM_W1, P.rho_in), w5 = mul(LBM_W5, P.rho_in);
-                    double *v = cluster.map_shared_rank(sm, 0) + dofs + y;   // row 0
-                    v[1 * plane] = add(mul(w1, p[1]), sub(o[1], e[1]));
-                    v[5 * plane] = add(mul(w5, p[5]), sub(o[5], e[5]));
-                    v[8 * plane] = add(mul(w5, p[8]), sub(o[8], e[8]));
+            for (int m = g; m < g + G; m++)
+#pragma unroll
+                for (int i = 0; i < 9; i++) f[m][i] = dsmem_ld(src[m][i] + so);
+            if (MASK) {
+#pragma unroll
+                for (int m = g; m < g + G; m++) {
+                    const unsigned td = todo[m];
+                    if (!td) continue;               // fluid cells and plain bounce-back (rigid walls): nothing to patch
+                    const double *oc = Q.ob[s & 1];
+#pragma unroll
+                    for (int i = 1; i < 9; i++)
+                        if ((td >> i) & 1) f[m][i] = sub(f[m][i], P.ktab[(kd[m].rule[i] >> 3) * 9 + kopp[i]]);
+                    if (td >> 9) {
+#pragma unroll
+                        for (int i = 0; i < 9; i++)
+                            if ((td >> (9 + i)) & 1) f[m][i] = P.ctab[(kd[m].rule[i] >> 3) * 9 + i];
+                        if ((td >> 21) & 1) f[m][3] = __ldcg(oc + 0 * P.pitch + cy_[m]);
+                        if ((td >> 24) & 1) f[m][6] = __ldcg(oc + 1 * P.pitch + cy_[m]);
+                        if ((td >> 25) & 1) f[m][7] = __ldcg(oc + 2 * P.pitch + cy_[m]);
+                    }
                 }
-                if (flags & LBM_CELL_PBC_OUT_SRC) {
-                    const double w1 = mul(LBM_W1, P.rho_out), w5 = mul(LBM_W5, P.rho_out);
-                    double *v = cluster.map_shared_rank(sm, (NX - 1) / R) + dofs + ((NX - 1) % R) * NY + y;   // row NX-1
-                    v[3 * plane] = add(mul(w1, p[3]), sub(o[3], e[3]));
-                    v[6 * plane] = add(mul(w5, p[6]), sub(o[6], e[6]));
-                    v[7 * plane] = add(mul(w5, p[7]), sub(o[7], e[7]));
+            }
+            // branch-free division / square root (lbm_device.cuh): the dependent chain of ONE cell update is what a step of
+            // this kernel waits for, and two cells of a thread interleave; operands the fast paths reject redo the moments
+            // with the library operations
+            double rho[M], ux[M], uy[M], p[M][9];
+            bool slow[M];
+#pragma unroll
+            for (int m = g; m < g + G; m++) {
+                slow[m] = false;
+                moments_fast(f[m], rho[m], ux[m], uy[m], slow[m]);
+                eq_poly_fast(ux[m], uy[m], p[m], slow[m]);
+            }
+#pragma unroll
+            for (int m = g; m < g + G; m++) {
+                if (slow[m]) {
+                    moments(f[m], rho[m], ux[m], uy[m]);
+                    eq_poly(ux[m], uy[m], p[m]);
+                }
+            }
+#pragma unroll
+            for (int m = g; m < g + G; m++) {
+                if (!act[m]) continue;
+                const int y = cy_[m];
+                if (P.probe && cx_[m] == P.px && y == P.py) {
+                    const long long t_new = tc0 + s + 1;
+                    double *slot = P.probe + 2 * (t_new % P.probe_cap);
+                    slot[0] = ux[m];
+                    slot[1] = uy[m];
+                    publish_progress(P, t_new);
+                }
+                double e[9], o[9];
+                eq_from_poly(rho[m], p[m], e);
+                collide(f[m], e, P.omega, o);
+                const unsigned flags = MASK ? kd[m].flags : 0u, skip = MASK ? kd[m].skip_store : 0u;
+                if (MASK && (flags & LBM_CELL_OUTLET_SRC)) {
+                    double *on = Q.ob[(s + 1) & 1];
+                    __stcg(on + 0 * P.pitch + y, f[m][3]);
+                    __stcg(on + 1 * P.pitch + y, f[m][6]);
+                    __stcg(on + 2 * P.pitch + y, f[m][7]);
+                    __threadfence();
+                }
+                double *w = sm + dofs + cq[m];
+                if (!MASK || skip == 0) {
+#pragma unroll
+                    for (int i = 0; i < 9; i++) w[i * plane] = o[i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 9; i++)
+                        if (!((skip >> i) & 1)) w[i * plane] = o[i];
+                }
+                if (MASK && (flags & (LBM_CELL_PBC_IN_SRC | LBM_CELL_PBC_OUT_SRC))) {
+                    // periodic_with_pressure_variations (boundary_conditions.py:337-344), see store_pbc: the virtual rows 0 and
+                    // NX-1 belong to the first / last CTA of the cluster
+                    if (flags & LBM_CELL_PBC_IN_SRC) {
+                        const double w1 = mul(LBM_W1, P.rho_in), w5 = mul(LBM_W5, P.rho_in);
+                        double *v = cluster.map_shared_rank(sm, 0) + dofs + y;   // row 0
+                        v[1 * plane] = add(mul(w1, p[m][1]), sub(o[1], e[1]));
+                        v[5 * plane] = add(mul(w5, p[m][5]), sub(o[5], e[5]));
+                        v[8 * plane] = add(mul(w5, p[m][8]), sub(o[8], e[8]));
+                    }
+                    if (flags & LBM_CELL_PBC_OUT_SRC) {
+                        const double w1 = mul(LBM_W1, P.rho_out), w5 = mul(LBM_W5, P.rho_out);
+                        double *v = cluster.map_shared_rank(sm, C - 1) + dofs + (NX - 1 - lo(C - 1)) * NY + y;   // row NX-1
+                        v[3 * plane] = add(mul(w1, p[m][3]), sub(o[3], e[3]));
+                        v[6 * plane] = add(mul(w5, p[m][6]), sub(o[6], e[6]));
+                        v[7 * plane] = add(mul(w5, p[m][7]), sub(o[7], e[7]));
+                    }
                 }
             }
         }
@@ -1143,7 +1195,6 @@ __global__ void __launch_bounds__(TMAX, 1) k_cluster_steps(const __grid_constant
         *((n & 1) ? t_dst : t_src) = tc0 + n;
         *((n & 1) ? t_src : t_dst) = tc0 + n - 1;
     }
-    (void)C;
 }
 
 // -------------------------------------------------------------------------------------------------------

@@ -20,7 +20,9 @@ python tools/make_traffic_json.py $OUT/${TAG}_k_stepNx3_full.csv $OUT/${TAG}_k_s
 # 3. BC-bearing workload with two steps per pass: launch list (k_step2x on the clean rows + mask launches on the strips)
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:k_step -s 2 -c 16 --csv \
     --log-file $OUT/${TAG}_karman_fused.csv $BENCH --workload karman > $OUT/${TAG}_karman_fused.log 2>&1
-# 4. the cluster kernel on config 1 (100 x 50, 2000 steps in one launch)
-ncu --set full --clock-control none -k regex:k_cluster -c 1 -o $OUT/${TAG}_k_cluster -f python tools/profile_cluster.py > $OUT/${TAG}_k_cluster.log 2>&1
-ncu -i $OUT/${TAG}_k_cluster.ncu-rep --page raw --csv > $OUT/${TAG}_k_cluster_full.csv 2>/dev/null
+# 4. the cluster kernel on configs 1-3 (100 x 50 periodic, 100 x 100 Couette, 100 x 50 Poiseuille; 2000 steps in one launch)
+for c in periodic couette poiseuille; do
+  ncu --set full --clock-control none --import-source on -k regex:k_cluster -c 1 -o $OUT/${TAG}_k_cluster_$c -f python tools/profile_cluster.py $c > $OUT/${TAG}_k_cluster_$c.log 2>&1
+  ncu -i $OUT/${TAG}_k_cluster_$c.ncu-rep --page raw --csv > $OUT/${TAG}_k_cluster_${c}_full.csv 2>/dev/null
+done
 ls -la $OUT
