@@ -124,11 +124,15 @@ struct lbm_ctx {
     struct GraphEntry {
         double omega;
         int parity, mode;
+        bool snap_last;      // the last captured step keeps the ghost snapshot (a call that ENDS on this replay)
         const void *probe;
         cudaGraphExec_t exec;
         long long launches;
     };
     std::vector<GraphEntry> graphs;
+    // The ghost-ring snapshot (snapshot_ghosts) serves the materialisation after a call's LAST step only: every other
+    // step of a call skips it (a load round trip + stores on the edge threads of a launch-bound step).
+    bool skip_snap = false;
     bool use_graphs = true;
     bool pdl = true;              // programmatic dependent launch between the step kernels of launch-bound lattices (option "pdl")
     bool use_fused = true;        // LBM_NO_FUSED=1: one step per pass only (A/B measurements)
@@ -858,6 +862,7 @@ static void fill_common(const lbm_ctx *c, StepParams &P, int src_buf, int dst_bu
     P.px = -1;
     P.py = -1;
     P.snap_row = c->snap_row;
+    P.no_snap = c->skip_snap ? 1 : 0;
     P.snap_col = c->snap_col;
     P.cells = c->cells;
     P.n_cells = c->n_cells;
@@ -963,7 +968,8 @@ static int rows_launch(lbm_ctx *c, StepParams P, int row0a, int na, int row0b, i
         dim3 grid((pairs + pbs - 1) / pbs, na);
         // (the pair kernel has no prologue to overlap: early-launched blocks only take slots away below ~2^17 cells,
         //  profiles/r01e_small_lattices_pdl.txt)
-        e = launch_kernel(k_step_pair, grid, dim3(pbs), st, use_pdl(c) && (long long)c->NX * c->NY >= (1 << 17), P);
+        const long long cells = (long long)c->NX * c->NY;
+        e = launch_kernel(cells <= (1 << 19) ? k_step_pair<true> : k_step_pair<false>, grid, dim3(pbs), st, use_pdl(c) && cells >= (1 << 17), P);
     } else if (mask)
         e = halo ? launch<true, true, false, false>(P, blocks, bs, st, use_pdl(c)) : launch<true, false, false, false>(P, blocks, bs, st, use_pdl(c));
     else
@@ -1452,11 +1458,11 @@ static void drop_graphs(lbm_ctx *c)
     c->graphs.clear();
 }
 
-static int graph_for(lbm_ctx *c, double omega, lbm_ctx::GraphEntry **out)
+static int graph_for(lbm_ctx *c, double omega, bool snap_last, lbm_ctx::GraphEntry **out)
 {
     const int mode = c->bc_mode;
     for (auto &g : c->graphs)
-        if (g.omega == omega && g.parity == c->cur && g.mode == mode && g.probe == (const void *)c->probe) {
+        if (g.omega == omega && g.parity == c->cur && g.mode == mode && g.snap_last == snap_last && g.probe == (const void *)c->probe) {
             *out = &g;
             return LBM_OK;
         }
@@ -1465,7 +1471,11 @@ static int graph_for(lbm_ctx *c, double omega, lbm_ctx::GraphEntry **out)
     const long long l0 = c->launches;
     CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
     int rc = LBM_OK, src = c->cur;
-    for (int i = 0; i < kGraphSteps && rc == LBM_OK; i++, src ^= 1) rc = one_step(c, src, omega, 0);
+    for (int i = 0; i < kGraphSteps && rc == LBM_OK; i++, src ^= 1) {
+        c->skip_snap = !(snap_last && i == kGraphSteps - 1);
+        rc = one_step(c, src, omega, 0);
+    }
+    c->skip_snap = false;
     cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
     const long long per_graph = c->launches - l0;
     c->launches = l0;
@@ -1478,7 +1488,7 @@ static int graph_for(lbm_ctx *c, double omega, lbm_ctx::GraphEntry **out)
     e = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) return fail(LBM_ERR_CUDA, "graph instantiation failed: %s", cudaGetErrorString(e));
-    c->graphs.push_back({omega, c->cur, mode, (const void *)c->probe, exec, per_graph});
+    c->graphs.push_back({omega, c->cur, mode, snap_last, (const void *)c->probe, exec, per_graph});
     *out = &c->graphs.back();
     return LBM_OK;
 }
@@ -1573,9 +1583,9 @@ extern "C" int lbm_step(lbm_ctx *c, double omega, int n_steps)
         }
     }
     if (c->use_graphs && !c->any_remote && (long long)c->NX * c->NY < kEdgeThreshold && left >= 2 * kGraphSteps) {
-        lbm_ctx::GraphEntry *g = nullptr;
-        if (int rc = graph_for(c, omega, &g)) return rc;
         while (left >= kGraphSteps) {
+            lbm_ctx::GraphEntry *g = nullptr;
+            if (int rc = graph_for(c, omega, left == kGraphSteps, &g)) return rc;   // (the entry may move: look it up per replay)
             CK(cudaGraphLaunch(g->exec, c->stream));
             c->launches += g->launches;
             c->t += kGraphSteps;
@@ -1606,7 +1616,10 @@ extern "C" int lbm_step(lbm_ctx *c, double omega, int n_steps)
         }
     }
     for (int i = 0; i < left; i++) {
-        if (int rc = one_step(c, c->cur, omega, c->t + 1)) return rc;
+        c->skip_snap = i + 1 < left;
+        const int rc = one_step(c, c->cur, omega, c->t + 1);
+        c->skip_snap = false;
+        if (rc) return rc;
         c->cur ^= 1;
         c->t++;
         c->last_depth = 1;

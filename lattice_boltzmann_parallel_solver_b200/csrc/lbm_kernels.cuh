@@ -137,26 +137,6 @@ __device__ __forceinline__ void snapshot_ghosts(const StepParams &P, int x, int 
     }
 }
 
-// f_post of one fluid cell: nine pulls with periodic wrap over the local array (np.roll semantics)
-__device__ __forceinline__ void pull_fluid(const StepParams &P, int x, int y, double (&f)[9])
-{
-    const int xm = x == 0 ? P.NX - 1 : x - 1, xp = x == P.NX - 1 ? 0 : x + 1;
-    const int ym = y == 0 ? P.NY - 1 : y - 1, yp = y == P.NY - 1 ? 0 : y + 1;
-    const double *r0 = P.src + srow(P, x) * P.pitch;
-    const double *rm = P.src + srow(P, xm) * P.pitch;
-    const double *rp = P.src + srow(P, xp) * P.pitch;
-    const long long pl = P.plane;
-    f[0] = ldS(r0 + y);
-    f[1] = ldS(rm + pl + y);
-    f[2] = ldS(r0 + 2 * pl + ym);
-    f[3] = ldS(rp + 3 * pl + y);
-    f[4] = ldS(r0 + 4 * pl + yp);
-    f[5] = ldS(rm + 5 * pl + ym);
-    f[6] = ldS(rp + 6 * pl + ym);
-    f[7] = ldS(rp + 7 * pl + yp);
-    f[8] = ldS(rm + 8 * pl + yp);
-}
-
 // f_post[I] of a non-fluid cell by its rule (rule table of include/lbm_b200.h). I is a compile-time index so that
 // the nine results stay in registers: no out-of-line call, no local-memory array anywhere in the step kernels.
 template <int I>
@@ -328,24 +308,43 @@ __device__ __forceinline__ void publish_progress(const StepParams &P, long long 
     *(volatile long long *)P.progress = t_new;
 }
 
-__device__ __forceinline__ void record_probe(const StepParams &P, double ux, double uy)
+// One-step launches keep the system-scope fence off the step's critical path (it cost 0.9 us of a 4 us von Karman step):
+// the sample of time t and the device clock are plain stores, and the time word the host polls is advanced by the
+// probe thread of the NEXT launch — probe_prologue, right after the dependent-launch wait, i.e. when the launch that
+// wrote the sample has completed and flushed. The newest sample of a drained stream needs no word at all
+// (lbm_probe_read falls back to "both streams idle").
+__device__ __forceinline__ long long probe_prologue(const StepParams &P)
 {
-    const long long t_new = __ldcg(P.tc_in) + 1;
+    const long long t_in = __ldcg(P.tc_in);
+    *(volatile long long *)P.progress = t_in;
+    return t_in;
+}
+
+__device__ __forceinline__ void record_probe(const StepParams &P, double ux, double uy, long long t_in)
+{
+    const long long t_new = t_in + 1;
     double *slot = P.probe + 2 * (t_new % P.probe_cap);
     slot[0] = ux;
     slot[1] = uy;
     *P.tc_out = t_new;
-    publish_progress(P, t_new);
 }
 
 // Everything one cell does after its nine f_post values are known (shared by the register-resident fluid path
 // and the out-of-line rule path).
 template <bool HALO, bool FINAL>
 __device__ __forceinline__ void finish_cell(const StepParams &P, int x, int y, const double (&f)[9], unsigned flags,
-                                            unsigned skip)
+                                            unsigned skip, bool is_probe, long long t_in)
 {
-    double rho, ux, uy;
-    moments(f, rho, ux, uy);
+    // branch-free division / square root (lbm_device.cuh): on launch-bound lattices a step IS the dependent chain of one
+    // cell update; operands the fast paths reject (never in a physical run) take the library operations
+    double rho, ux, uy, p[9];
+    bool slow = false;
+    moments_fast(f, rho, ux, uy, slow);
+    if (!FINAL) eq_poly_fast(ux, uy, p, slow);
+    if (slow) {
+        moments(f, rho, ux, uy);
+        if (!FINAL) eq_poly(ux, uy, p);
+    }
     if (FINAL) {
         const long long o = (long long)(x - P.ox0) * P.ow + (y - P.oy0);
         if (P.o_f) {
@@ -359,9 +358,8 @@ __device__ __forceinline__ void finish_cell(const StepParams &P, int x, int y, c
         }
         return;
     }
-    if (P.probe && x == P.px && y == P.py) record_probe(P, ux, uy);
-    double p[9], e[9], s[9];
-    eq_poly(ux, uy, p);
+    if (is_probe) record_probe(P, ux, uy, t_in);
+    double e[9], s[9];
     eq_from_poly(rho, p, e);
     collide(f, e, P.omega, s);
     if (flags & LBM_CELL_OUTLET_SRC) {
@@ -394,11 +392,49 @@ __device__ __forceinline__ void step_cell(const StepParams &P, int x, int y, uns
 {
     double f[9];
     unsigned flags = 0, skip = 0;
-    if (kind != 0) {
+    const bool is_probe = !FINAL && P.probe && x == P.px && y == P.py;
+    const long long t_in = is_probe ? probe_prologue(P) : 0;
+    if (!(FINAL && P.use_snap)) {
+        // ONE load per population for every kind of cell: the address is the streamed neighbour's (fluid cells, PULL
+        // rules), the cell's own opposite population (bounce-back), the inlet constant in the table or the outlet side
+        // buffer. A warp that holds boundary cells decodes their rules (integer work on a few lanes) and then issues
+        // the same nine loads as every other warp — one L2 round trip instead of two (the rule lanes' pulls and the
+        // fluid lanes' pulls used to run one after the other), which is what a step of a launch-bound lattice costs.
+        constexpr int opp[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
+        const int xm = x == 0 ? P.NX - 1 : x - 1, xp = x == P.NX - 1 ? 0 : x + 1;
+        const int ym = y == 0 ? P.NY - 1 : y - 1, yp = y == P.NY - 1 ? 0 : y + 1;
+        const long long pl = P.plane;
+        const double *r0 = P.src + srow(P, x) * P.pitch, *rm = P.src + srow(P, xm) * P.pitch, *rp = P.src + srow(P, xp) * P.pitch;
+        const double *a[9] = {r0 + y,           rm + pl + y,      r0 + 2 * pl + ym, rp + 3 * pl + y, r0 + 4 * pl + yp,
+                              rm + 5 * pl + ym, rp + 6 * pl + ym, rp + 7 * pl + yp, rm + 8 * pl + yp};
+        double kv[9] = {};   // wall-velocity terms of moving_wall (boundary_conditions.py:207-210), 0 elsewhere
+        if (kind != 0) {
+            flags = k.flags;
+            skip = k.skip_store;
+#pragma unroll
+            for (int i = 0; i < 9; i++) {
+                const int r = k.rule[i], type = r & 7, row = r >> 3;
+                if (type == LBM_RULE_BOUNCE) {
+                    a[i] = r0 + opp[i] * pl + y;
+                    if (row) kv[i] = P.ktab[row * 9 + opp[i]];
+                } else if (type == LBM_RULE_CONST) {
+                    a[i] = P.ctab + row * 9 + i;
+                } else if (type == LBM_RULE_OUTLET) {   // populations 3, 6, 7 -> slots 0, 1, 2 of the side buffer
+                    a[i] = P.out_cur + (i == 3 ? 0 : (i == 6 ? 1 : 2)) * P.pitch + y;
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 9; i++) f[i] = ldS(a[i]);
+        if (kind != 0) {
+#pragma unroll
+            for (int i = 1; i < 9; i++) f[i] = sub(f[i], kv[i]);   // v - (+0.0) == v for every v
+        }
+    } else if (kind != 0) {   // materialisation of a block with ghost cells: ghosts come from the snapshot (ld_cell)
         pull_rules(P, k, x, y, f);
         flags = k.flags;
         skip = k.skip_store;
-    } else if (FINAL && P.use_snap) {
+    } else {
         constexpr int cx[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1}, cy[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
 #pragma unroll
         for (int i = 0; i < 9; i++) {
@@ -407,10 +443,8 @@ __device__ __forceinline__ void step_cell(const StepParams &P, int x, int y, uns
             ys = ys < 0 ? P.NY - 1 : (ys >= P.NY ? 0 : ys);
             f[i] = ld_cell(P, i, xs, ys);
         }
-    } else {
-        pull_fluid(P, x, y, f);
     }
-    finish_cell<HALO, FINAL>(P, x, y, f, flags, skip);
+    finish_cell<HALO, FINAL>(P, x, y, f, flags, skip, is_probe, t_in);
 }
 
 template <bool MASK, bool HALO, bool FINAL, bool LIST>
@@ -465,6 +499,10 @@ __device__ __forceinline__ void st2(double *p, double a, double b)
     asm volatile("st.global.cg.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
 }
 
+// ILP: both cells of the pair in one basic block (branch-free arithmetic; 119 registers) — lattices whose step is bound by
+// the latency of one cell update (up to 2^19 cells: 512^2 5.46 -> 5.31 us, 256^2 3.33 -> 3.01). Larger lattices keep the
+// lean version (more resident warps: 1000^2 21.4 us vs 23.3 with ILP; 16384^2 5.66 ms either way).
+template <bool ILP>
 __global__ void __launch_bounds__(256) k_step_pair(const __grid_constant__ StepParams P)
 {
     pdl_release();
@@ -479,6 +517,8 @@ __global__ void __launch_bounds__(256) k_step_pair(const __grid_constant__ StepP
     const double *r0 = P.src + (long long)x * P.pitch;
     const double *rm = P.src + (long long)xm * P.pitch;
     const double *rp = P.src + (long long)xp * P.pitch;
+    const bool is_probe = P.probe && x == P.px && (y == P.py || y + 1 == P.py);
+    const long long t_in = is_probe ? probe_prologue(P) : 0;
 
     double fa[9], fb[9];
     {
@@ -495,23 +535,34 @@ __global__ void __launch_bounds__(256) k_step_pair(const __grid_constant__ StepP
         fa[7] = ldS(rp + 7 * pl + y + 1); fb[7] = ldS(rp + 7 * pl + yq);
         fa[8] = ldS(rm + 8 * pl + y + 1); fb[8] = ldS(rm + 8 * pl + yq);
     }
-    double sa[9], sb[9];
-    {
-        double rho, ux, uy, p[9], e[9];
-        moments(fa, rho, ux, uy);
-        if (P.probe && x == P.px && y == P.py) record_probe(P, ux, uy);
-        eq_poly(ux, uy, p);
-        eq_from_poly(rho, p, e);
-        collide(fa, e, P.omega, sa);
+    // both cells in one basic block (branch-free division / square root, lbm_device.cuh): their dependent chains
+    // interleave, which is most of what a step of a launch-bound lattice waits for
+    double sa[9], sb[9], uax, uay, ubx, uby;
+    if (ILP) {
+        bool slow_a = false, slow_b = false;
+        relax_fast(fa, P.omega, sa, uax, uay, slow_a);
+        relax_fast(fb, P.omega, sb, ubx, uby, slow_b);
+        if (slow_a | slow_b) {   // operands outside the fast paths' range: never in a physical run
+            if (slow_a) relax_redo(fa, P.omega, sa, uax, uay);
+            if (slow_b) relax_redo(fb, P.omega, sb, ubx, uby);
+        }
+    } else {
+        {
+            double rho, p[9], e[9];
+            moments(fa, rho, uax, uay);
+            eq_poly(uax, uay, p);
+            eq_from_poly(rho, p, e);
+            collide(fa, e, P.omega, sa);
+        }
+        {
+            double rho, p[9], e[9];
+            moments(fb, rho, ubx, uby);
+            eq_poly(ubx, uby, p);
+            eq_from_poly(rho, p, e);
+            collide(fb, e, P.omega, sb);
+        }
     }
-    {
-        double rho, ux, uy, p[9], e[9];
-        moments(fb, rho, ux, uy);
-        if (P.probe && x == P.px && y + 1 == P.py) record_probe(P, ux, uy);
-        eq_poly(ux, uy, p);
-        eq_from_poly(rho, p, e);
-        collide(fb, e, P.omega, sb);
-    }
+    if (is_probe) record_probe(P, y == P.py ? uax : ubx, y == P.py ? uay : uby, t_in);
     double *d = P.dst + (long long)x * P.pitch + y;
 #pragma unroll
     for (int i = 0; i < 9; i++) st2(d + i * pl, sa[i], sb[i]);
@@ -1134,7 +1185,9 @@ __global__ void __launch_bounds__(TMAX, 1) k_cluster_steps(const __grid_constant
                     double *slot = P.probe + 2 * (t_new % P.probe_cap);
                     slot[0] = ux[m];
                     slot[1] = uy[m];
-                    publish_progress(P, t_new);
+                    // the time word the host polls: every 32nd step only — its system-scope fence holds up this
+                    // thread, hence (cluster barrier) every CTA, for ~1 us; the samples of a finished launch need no word
+                    if ((s & 31) == 31) publish_progress(P, t_new);
                 }
                 double e[9], o[9];
                 eq_from_poly(rho[m], p[m], e);
