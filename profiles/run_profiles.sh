@@ -22,7 +22,9 @@ ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum 
     --log-file $OUT/${TAG}_karman_fused.csv $BENCH --workload karman > $OUT/${TAG}_karman_fused.log 2>&1
 # 4. the cluster kernel on configs 1-3 (100 x 50 periodic, 100 x 100 Couette, 100 x 50 Poiseuille; 2000 steps in one launch)
 for c in periodic couette poiseuille; do
-  ncu --set full --clock-control none --import-source on -k regex:k_cluster -c 1 -o $OUT/${TAG}_k_cluster_$c -f python tools/profile_cluster.py $c > $OUT/${TAG}_k_cluster_$c.log 2>&1
+  ncu --set full --clock-control none -k regex:k_cluster -c 1 -o $OUT/${TAG}_k_cluster_$c -f python tools/profile_cluster.py $c > $OUT/${TAG}_k_cluster_$c.log 2>&1
   ncu -i $OUT/${TAG}_k_cluster_$c.ncu-rep --page raw --csv > $OUT/${TAG}_k_cluster_${c}_full.csv 2>/dev/null
 done
+# gpurun brings back at most 64 MiB: keep the report of the headline kernel only (the CSV pages of the others are above)
+rm -f $OUT/${TAG}_k_step2x.ncu-rep $OUT/${TAG}_k_step_pair.ncu-rep $OUT/${TAG}_k_cluster_*.ncu-rep
 ls -la $OUT
