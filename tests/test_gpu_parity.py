@@ -375,6 +375,38 @@ def test_config4_karman_native_run_with_probe(P, oracle):
     lat.close()
 
 
+@pytest.mark.parametrize('calls', [(64,), (96, 32), (33, 31), (1, 1, 62), (40, 64, 1)])
+def test_ghost_ring_results_after_calls_that_end_on_a_graph_replay(P, oracle, calls):
+    """The ghost-ring snapshot that materialisation reads is taken on the LAST step of a call only — also when that step
+    sits at the end of a replayed CUDA graph (second graph variant) — and the probe's time word lags one launch behind:
+    fields and probe samples after every call equal the C oracle (parallel von Karman block with its own ghost ring)."""
+    from lattice_boltzmann_parallel_solver_b200.engine import Lattice
+    lx, ly, d = 62, 40, 8
+    rng = np.random.default_rng(21)
+    shape = (lx + 2, ly + 2)
+    rho = rng.uniform(0.9, 1.1, shape); u = rng.uniform(-0.05, 0.05, shape + (2,)); f = oracle.np.equilibrium(rho, u)
+    bc = P.boundary_utils.parallel_von_karman_boundary_conditions([0, 0], lx, ly, lx, ly, 1, 1, 1.0, 0.1, d)
+    lat = Lattice(*shape, bc.kind_map(shape), ghost=(1, 1))
+    lat.connect_self_periodic()
+    px, py = 3 * lx // 4 + 1, ly // 2 + 1
+    lat.probe(px, py, capacity=512)
+    lat.load(f, rho, u, 1.6)
+    scen = oracle.c.karman(lx, ly, 1.0, 0.1, d, ghost=1)
+    state, t = (f, rho, u), 0
+    samples = []
+    for n in calls:
+        lat.run(n)
+        for _ in range(n):
+            state = oracle.c.run(*state, 1.6, scen, 1)
+            samples.append(state[2][px, py].copy())
+        t += n
+        assert np.array_equal(lat.probe_read(t - n + 1, n), np.array(samples[t - n:t])), (calls, t)
+        got = lat.fields()
+        for a, b, name in zip(got, state, ('f', 'rho', 'u')):
+            assert np.array_equal(a, b), (calls, t, name)
+    lat.close()
+
+
 def test_karman_serial_rigid_object(P, oracle):
     """milestoneQuickFunctionCalls.py:304-320 — inlet, outlet and rigid_object composed by hand, no ghost ring."""
     L, B, BU = P.lattice_boltzmann_method, P.boundary_conditions, P.boundary_utils
