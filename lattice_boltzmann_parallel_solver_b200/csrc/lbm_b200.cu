@@ -1074,7 +1074,7 @@ static int pick_seg(const lbm_ctx *c, int rows, int depth = 2)
     int seg = 256;
     while (seg > 8 && strips * ((rows + seg - 1) / seg) < 2000) seg /= 2;
     if (seg < 128 || !c->wave_seg) return seg;
-    const long long slots = (long long)c->n_sm * (deep ? (depth == 2 ? 3 : 2) : 4);
+    const long long slots = (long long)c->n_sm * (deep ? (depth == 2 ? 3 : 2) * (kDeepThreads <= 64 ? 128 / kDeepThreads : 1) : 4);
     double best_eff = 0;
     int best = seg;
     for (int ns = (rows + 511) / 512; ns <= (rows + 127) / 128; ns++) {      // segments of 128 .. 512 rows
