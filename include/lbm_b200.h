@@ -155,8 +155,8 @@ int lbm_set_bc_mode(lbm_ctx *ctx, int mode);
  *   "l2_prefetch"    (2) rows ahead of its march whose source segments the multi-step kernel prefetches into L2 with
  *                    cp.async.bulk.prefetch; 0 = off
  *   "fused_seg"      (0) output rows per thread block of the multi-step kernel; 0 = 8..512 by lattice size
- *   "cluster"        (1) lattices that fit the distributed shared memory of one thread-block cluster (8 CTAs; up to ~12 000
- *                    cells, no ghost ring) take ALL steps of a call in one launch of k_cluster_steps: the lattice stays in
+ *   "cluster"        (1) lattices that fit the distributed shared memory of one thread-block cluster (16 CTAs, 8 where 16 cannot
+ *                    be scheduled; up to ~25 000 cells, no ghost ring) take ALL steps of a call in one launch of k_cluster_steps: the lattice stays in
  *                    shared memory, a step ends with a hardware cluster barrier instead of a kernel boundary. 1 = the first
  *                    four eligible calls are timed alternately on this path and on graph replay and the faster one is kept
  *                    (same bits either way); 2 = always where the lattice fits; 0 = never
