@@ -776,7 +776,7 @@ struct Deep {
     static constexpr int W = 2 * T - 4 * (D - 1);   // output columns per block
     static constexpr int RS = 2 * T;                // doubles per ring row
     static constexpr int SP = 18;                   // slot-populations per ring
-    static constexpr int MINB = (D == 2 ? 3 : 2) * (T <= 64 ? 128 / T : 1);   // resident blocks per SM the kernel is compiled for (D >= 3: 8 warps, 255 registers)
+    static constexpr int MINB = D == 2 ? 3 : 2;     // resident blocks per SM the kernel is compiled for (D >= 3: 255 registers)
     static constexpr int SMEM = (D - 1) * SP * RS * (int)sizeof(double);
 };
 
