@@ -65,6 +65,8 @@ class Lattice:
         self._probe_t0 = 0            # samples exist for device times > _probe_t0
         self._probe_auto = False      # configured by _probe_sample, not by the caller
         self._watch = None            # (x, y, t) of the last velocity cell read
+        self._probe_buf = None        # (array, pointer) of _probe_cell
+        self._shapes = {k: fn(self.nx, self.ny) for k, fn in _SHAPES.items()}
         # lazy-handle bookkeeping (see module docstring)
         self._pending = None          # omega of the steps requested but not yet launched
         self._pending_n = 0           # how many of them
@@ -193,6 +195,17 @@ class Lattice:
         N.check(self.lib.lbm_probe_read(self._ctx, int(t0), int(n), N.dptr(out)))
         return out
 
+    def _probe_cell(self, t):
+        """One sample through a preallocated buffer (the per-step read of a driver loop: no allocation, no pointer cast)."""
+        buf = self._probe_buf
+        if buf is None:
+            arr = np.empty((1, 2))
+            buf = self._probe_buf = (arr, N.dptr(arr))
+        rc = self.lib.lbm_probe_read(self._ctx, t, 1, buf[1])
+        if rc:
+            N.check(rc)
+        return buf[0][0].copy()
+
     def _probe_sample(self, x, y, t):
         """(u_x, u_y) of cell (x, y) at the current device time t from the probe ring, or None when the ring does not
         hold it. The reference's drivers read ONE velocity cell after every step (experiments.py:703-704): the second
@@ -204,7 +217,7 @@ class Lattice:
             return None                               # ghost cells are not computed by the step kernels
         p = self._probe
         if p is not None and p[0] == x and p[1] == y and t > self._probe_t0:
-            return self.probe_read(t, 1)[0]
+            return self._probe_cell(t)
         if (p is None or self._probe_auto) and self._watch == (x, y, t - 1):
             self.probe(x, y, capacity=AUTO_PROBE_CAPACITY)
             self._probe_auto = True
@@ -420,8 +433,9 @@ class LatticeArray(np.lib.mixins.NDArrayOperatorsMixin):
         self._value = None
         self._hist = None             # _HistorySlot while the field is parked on the device
         self._dirty = False           # written through __setitem__: the device copy no longer matches
-        self.shape = _SHAPES[which](lattice.nx, lattice.ny)
-        self.dtype = np.dtype(np.float64)
+        self.shape = lattice._shapes[which]
+
+    dtype = np.dtype(np.float64)
 
     ndim = property(lambda self: len(self.shape))
     size = property(lambda self: int(np.prod(self.shape)))
