@@ -133,6 +133,7 @@ struct lbm_ctx {
     // The ghost-ring snapshot (snapshot_ghosts) serves the materialisation after a call's LAST step only: every other
     // step of a call skips it (a load round trip + stores on the edge threads of a launch-bound step).
     bool skip_snap = false;
+    bool eager_progress = false;   // lbm_step(.., 1): the probe sample's time word is published by the step itself
     bool use_graphs = true;
     bool pdl = true;              // programmatic dependent launch between the step kernels of launch-bound lattices (option "pdl")
     bool use_fused = true;        // LBM_NO_FUSED=1: one step per pass only (A/B measurements)
@@ -863,6 +864,7 @@ static void fill_common(const lbm_ctx *c, StepParams &P, int src_buf, int dst_bu
     P.py = -1;
     P.snap_row = c->snap_row;
     P.no_snap = c->skip_snap ? 1 : 0;
+    P.eager_progress = c->eager_progress ? 1 : 0;
     P.snap_col = c->snap_col;
     P.cells = c->cells;
     P.n_cells = c->n_cells;
@@ -1617,8 +1619,10 @@ extern "C" int lbm_step(lbm_ctx *c, double omega, int n_steps)
     }
     for (int i = 0; i < left; i++) {
         c->skip_snap = i + 1 < left;
+        c->eager_progress = n_steps == 1;
         const int rc = one_step(c, c->cur, omega, c->t + 1);
         c->skip_snap = false;
+        c->eager_progress = false;
         if (rc) return rc;
         c->cur ^= 1;
         c->t++;

@@ -66,6 +66,7 @@ struct StepParams {
     double *snap_row, *snap_col;
     int use_snap;              // FINAL launches: read ghost cells from the snapshot instead of S
     int no_snap;               // launches through a strip window: take no ghost snapshot (the source is not S)
+    int eager_progress;        // one-step call (a driver that reads the probe cell after EVERY step): publish the time word in this launch
     // fix-up list
     const int2 *cells;
     int n_cells;
@@ -327,6 +328,7 @@ __device__ __forceinline__ void record_probe(const StepParams &P, double ux, dou
     slot[0] = ux;
     slot[1] = uy;
     *P.tc_out = t_new;
+    if (P.eager_progress) publish_progress(P, t_new);   // the host is waiting for exactly this sample: do not make it wait for the stream to drain
 }
 
 // Everything one cell does after its nine f_post values are known (shared by the register-resident fluid path
