@@ -25,8 +25,8 @@ def ensure_process_group(backend=None):
     dist = _dist()
     if not dist.is_initialized():
         import torch
-        if backend is None:
-            backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+        if backend is None:   # LBM_DIST_BACKEND=gloo: several ranks on ONE GPU (NCCL refuses that; the halo itself is CUDA-IPC)
+            backend = os.environ.get('LBM_DIST_BACKEND') or ('nccl' if torch.cuda.is_available() else 'gloo')
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         if backend == 'nccl':
             torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
