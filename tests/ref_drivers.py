@@ -98,6 +98,29 @@ def main():
             assert len(sim) == 10, len(sim)
             res[tag] = np.array([np.asarray(a[0], dtype=float) for a in sim])
             assert res[tag].shape == (10, ly)
+        # (9) density evolution: a density column plotted every few steps (:55-99)
+        matplotlib.calls.clear()
+        E.plot_evolution_of_density(lattice_grid_shape=(18, 18), initial_p0=0.5, epsilon=0.08, omega=1.0, time_steps=100,
+                                    number_of_visualizations=10)
+        cols = [a for name, a, k in matplotlib.calls if name.endswith('.plot') and len(a) == 2 and np.ndim(a[1]) == 1 and len(a[1]) == 18]
+        res['density_evolution'] = np.array([np.asarray(a[1], dtype=float) for a in cols])
+        assert res['density_evolution'].shape[0] >= 10
+        # (10) Poiseuille profiles, area under the curve, pressure along the centre line, absolute error (:377-504)
+        if mode != 'fake':                                      # the fake library has no pressure-periodic boundary
+            matplotlib.calls.clear()
+            E.plot_poiseuille_flow_vel_vectors(lattice_grid_shape=(24, 12), omega=1.5, delta_p=0.002, time_steps=300)
+            lines = [np.asarray(a[0], dtype=float) for name, a, k in matplotlib.calls
+                     if name == 'plt.plot' and len(a) >= 2 and np.ndim(a[0]) == 1 and np.asarray(a[0]).dtype.kind == 'f']
+            res['poiseuille_vectors'] = np.concatenate([v.ravel() for v in lines])
+            assert len(lines) >= 3
+        # (11) the parallel von Karman driver on one rank: a velocity-magnitude frame every 100 steps through save_mpiio (:584-647)
+        matplotlib.calls.clear()
+        if mode == 'reference':     # the reference's save_mpiio needs MPI-IO (Cartcomm.Sub, MPI.File): on ONE rank it is np.save
+            E.save_mpiio = lambda comm, file_name, array: np.save(file_name, array)
+        E.plot_parallel_von_karman_vortex_street(lattice_grid_shape=(60, 36), plate_size=10, time_steps=201)
+        frames = [a[0] for name, a, k in matplotlib.calls if name == 'cm.viridis']
+        res['karman_frames'] = np.array(frames)
+        assert res['karman_frames'].shape == (3, 36, 60)
     # (6) main.py end to end (argparse -> experiments): couette_vectors with explicit sizes
     matplotlib.calls.clear()
     sys.argv = ['main.py', '-f', 'couette_vectors', '-l', '10', '12', '-t', '60', '-mwv', '0.03']

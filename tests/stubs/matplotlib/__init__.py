@@ -54,4 +54,7 @@ def use(*args, **kwargs):
 def __getattr__(name):
     if name.startswith('__'):
         raise AttributeError(name)
+    if name in ('cm', 'pyplot'):          # `from matplotlib import cm` must find the submodule, not a recorder
+        import importlib
+        return importlib.import_module('.' + name, __name__)
     return Anything('matplotlib.' + name)

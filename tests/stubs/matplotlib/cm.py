@@ -1,5 +1,14 @@
-"""TEST-ONLY stand-in for matplotlib.cm."""
-from . import Anything
+"""TEST-ONLY stand-in for matplotlib.cm. `viridis` is the one colour map the reference's drivers CALL on data
+(src/experiments.py:643): it records its argument and returns a grey RGBA array of the right shape."""
+import numpy as np
+
+from . import Anything, calls
+
+
+def viridis(a):
+    a = np.asarray(a, dtype=float)
+    calls.append(('cm.viridis', (a.copy(),), {}))
+    return np.stack([a, a, a, np.ones_like(a)], axis=-1)
 
 
 def __getattr__(name):

@@ -31,7 +31,7 @@ def _run(mode, out):
     return np.load(out)
 
 
-FAKE_LACKS = {'poiseuille_evolution'}     # tests/fake_native.py has no pressure-periodic boundary; the GPU run has it
+FAKE_LACKS = {'poiseuille_evolution', 'poiseuille_vectors'}     # tests/fake_native.py has no pressure-periodic boundary; the GPU run has it
 
 
 def _compare(ref, got, what):
