@@ -35,7 +35,9 @@ from . import _native as N
 
 HISTORY_BYTES = int(os.environ.get('LBM_HISTORY_MB', '256')) << 20   # device memory for kept-but-unread (rho, u) fields
 HISTORY_MAX_SLOTS = 1024
-MAX_DEFERRED = 64   # steps queued by lattice_boltzmann_step before they are launched as one batch
+# steps queued by lattice_boltzmann_step before they are launched as one batch: a multiple of the three steps of a pass
+# (64 left one slow single-step launch per batch on bandwidth-bound lattices) and of the 32 steps of a replayed graph
+MAX_DEFERRED = 96
 AUTO_PROBE_CAPACITY = 4096   # ring entries of the probe that velocity[px, py] reads configure by themselves
 
 
