@@ -60,34 +60,55 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe). The timed region of the
+    default run is ~60 ms, nvidia-smi needs longer than that to come up: the sampler is started before the warm-up steps,
+    polls every 20 ms, stamps every row with its arrival time, and reports the rows that arrived between begin() and
+    end() (falling back to the rows since the warm-up began — the same load — when the region was shorter than a poll)."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
 
     def __init__(self, gpu):
         self.gpu, self.rows, self.proc = gpu, [], None
+        self.t_begin = self.t_end = None
 
-    def start(self):
+    def start(self, wait_s=2.0):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '20'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            t0 = time.perf_counter()
+            while not self.rows and time.perf_counter() - t0 < wait_s and self.proc.poll() is None:
+                time.sleep(0.01)                      # nvidia-smi is up once its first row is here
         except Exception:
             self.proc = None
+        self.t_start = time.perf_counter()
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def begin(self):
+        self.t_begin = time.perf_counter()
+
+    def end(self):
+        self.t_end = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable'], 'samples': 0}
+        time.sleep(0.05)
         self.proc.terminate()
+        t_end = self.t_end if self.t_end is not None else time.perf_counter()
+        t_begin = self.t_begin if self.t_begin is not None else self.t_start
+        window = 'timed region'
+        rows = [r for t, r in self.rows if t_begin <= t <= t_end + 0.02]
+        if not rows:
+            window = 'warm-up + timed region (same load)'
+            rows = [r for t, r in self.rows if self.t_start <= t <= t_end + 0.02]
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             p = [c.strip() for c in r.split(',')]
             if len(p) < 9:
                 continue
@@ -100,7 +121,7 @@ class ClockSampler:
                 if v.lower().startswith('active'):
                     reasons.add(name)
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+                'reasons': sorted(reasons), 'samples': len(sm), 'window': window}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -501,17 +522,21 @@ def main():
         """`warmup` untimed steps, then exactly `steps` steps between CUDA events on the library's stream, bracketed by
         barrier + synchronize; max over ranks."""
         stream = torch.cuda.ExternalStream(lat.stream)
+        sampler = ClockSampler(local) if sample_clocks and rank == 0 else None
+        if sampler:
+            sampler.start()
         lat.run(warmup)
         lat.sync()
         barrier()
         l0 = lat.launches
-        sampler = ClockSampler(local) if sample_clocks and rank == 0 else None
-        if sampler:
-            sampler.start()
         torch.cuda.synchronize()
         barrier()
+        if sampler:
+            sampler.begin()
         ms = timed_steps(lat, stream, steps, all_max)
         torch.cuda.synchronize()
+        if sampler:
+            sampler.end()
         barrier()
         clocks = sampler.stop() if sampler else None
         cells_total = nx_local * world * ny
