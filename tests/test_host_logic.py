@@ -391,3 +391,41 @@ def test_karman_slab_kind_maps_equal_the_global_construction(monkeypatch):
             got = effective(bench.karman_slab_kind_map(nxg, ny, rank * nxl - g, nxl + 2 * g))
             for i in range(nxl + 2 * g):
                 assert got[i] == want[(rank * nxl - g + i) % nxg], (nxg, ny, world, rank, i)
+
+
+def test_clock_sampler_reports_the_rows_of_the_timed_region(tmp_path, monkeypatch):
+    """bench.ClockSampler against a stand-in nvidia-smi: rows that arrive between begin() and end() are the ones reported
+    (throttle reasons parsed); a region shorter than a poll falls back to the rows since the warm-up began."""
+    import stat
+    import time
+    import bench
+    fake = tmp_path / 'nvidia-smi'
+    fake.write_text('#!/bin/bash\n'
+                    'i=0\n'
+                    'while true; do\n'
+                    '  if [ $i -lt 5 ]; then echo "0, 345, 1965, 200.0, 0x0, Not Active, Not Active, Not Active, Not Active";\n'
+                    '  else echo "0, 1905, 1965, 990.0, 0x4, Not Active, Not Active, Not Active, Active"; fi\n'
+                    '  i=$((i+1)); sleep 0.02\n'
+                    'done\n')
+    fake.chmod(fake.stat().st_mode | stat.S_IEXEC)
+    monkeypatch.setenv('PATH', str(tmp_path) + os.pathsep + os.environ['PATH'])
+    s = bench.ClockSampler(0)
+    s.start()
+    assert s.rows, 'the first row is waited for'
+    time.sleep(0.15)          # "warm-up": the idle rows (345 MHz) pass
+    s.begin()
+    time.sleep(0.12)          # "timed region"
+    s.end()
+    got = s.stop()
+    assert got['window'] == 'timed region' and got['samples'] >= 3, got
+    assert got['sm_mhz'] == 1905.0 and got['sm_max_mhz'] == 1965.0 and got['reasons'] == ['sw_power_cap'], got
+    class Done:                # a region no poll fell into (nvidia-smi slower than the region): rows since the warm-up began
+        def terminate(self):
+            pass
+    s = bench.ClockSampler(0)
+    s.proc, s.t_start, s.t_begin, s.t_end = Done(), 10.0, 12.0, 12.05
+    s.rows = [(9.0, '0, 345, 1965, 200.0, 0x0, Not Active, Not Active, Not Active, Not Active'),
+              (11.0, '0, 1935, 1965, 990.0, 0x0, Not Active, Not Active, Not Active, Not Active'),
+              (13.0, '0, 345, 1965, 200.0, 0x0, Not Active, Not Active, Not Active, Not Active')]
+    got = s.stop()
+    assert got['samples'] == 1 and got['sm_mhz'] == 1935.0 and got['window'].startswith('warm-up') and got['reasons'] == [], got
