@@ -304,18 +304,20 @@ class Lattice:
         while self.time < goal:
             self._preserve(self.time)
             stop = goal
-            for t in sorted(self._handles):
-                if self.time < t < goal and any(h._value is None for h in self._live(t)):
-                    stop = t
-                    break
+            if goal - self.time > 1:                  # (a single step has no time in between to stop at)
+                for t in sorted(self._handles):
+                    if self.time < t < goal and any(h._value is None for h in self._live(t)):
+                        stop = t
+                        break
             n = stop - self.time
             omega = self._pending
             self._pending_n -= n
             if self._pending_n == 0:
                 self._pending = None
             self.run(n, omega)
-        for t in [t for t in self._handles if t < self.time and not self._live(t)]:
-            del self._handles[t]
+        if len(self._handles) > 1:
+            for t in [t for t in self._handles if t < self.time and not self._live(t)]:
+                del self._handles[t]
 
     def request_step(self, omega):
         """Called by lattice_boltzmann_step: queues one step and returns the three handles of its result."""
@@ -325,8 +327,9 @@ class Lattice:
         self._pending = omega
         self._pending_n += 1
         t = self.api_time
-        hs = tuple(LatticeArray(self, t, which) for which in ('f', 'rho', 'u'))
-        self._handles[t] = [weakref.ref(h) for h in hs]
+        ref = weakref.ref
+        hs = (LatticeArray(self, t, 'f'), LatticeArray(self, t, 'rho'), LatticeArray(self, t, 'u'))
+        self._handles[t] = [ref(hs[0]), ref(hs[1]), ref(hs[2])]
         return hs
 
     def reset_for_upload(self):
@@ -336,9 +339,11 @@ class Lattice:
         self._handles.clear()
 
     def is_current(self, *handles):
-        t = self.api_time
-        return all(isinstance(h, LatticeArray) and h._lattice is self and h._generation == self._generation and
-                   h._t == t and not h._dirty for h in handles)
+        t, g = self.time + self._pending_n, self._generation
+        for h in handles:
+            if not (type(h) is LatticeArray and h._lattice is self and h._generation == g and h._t == t and not h._dirty):
+                return False
+        return True
 
 
 def connect_blocks(blocks, dims):
@@ -427,6 +432,7 @@ class LatticeArray(np.lib.mixins.NDArrayOperatorsMixin):
     handle switches to a private writable copy and stops counting as the device's current state, so feeding it back
     into `lattice_boltzmann_step` uploads it."""
 
+    __slots__ = ('_lattice', '_t', '_which', '_generation', '_value', '_hist', '_dirty', 'shape', '__weakref__')
     __array_priority__ = 100
 
     def __init__(self, lattice, t, which):
@@ -527,12 +533,13 @@ class LatticeArray(np.lib.mixins.NDArrayOperatorsMixin):
             self.materialize().max(*a, **k)
 
     def __getitem__(self, index):
-        if self._on_device and isinstance(index, tuple) and len(index) >= 2:
+        if self._value is None and self._hist is None and type(index) is tuple and len(index) >= 2:
             ix, iy = index[0], index[1]
             if isinstance(ix, (int, np.integer)) and isinstance(iy, (int, np.integer)):
                 # velocity[px, py, ...] every step (experiments.py:703-704): fetch one cell, not the lattice
-                self._bring_current()
                 L = self._lattice
+                if self._t != L.time or self._generation != L._generation:
+                    self._bring_current()
                 if not (-L.nx <= ix < L.nx and -L.ny <= iy < L.ny):
                     raise IndexError(f'index ({ix}, {iy}) is out of bounds for a lattice of shape ({L.nx}, {L.ny})')
                 x, y = int(ix) % L.nx, int(iy) % L.ny
