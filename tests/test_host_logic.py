@@ -429,3 +429,18 @@ def test_clock_sampler_reports_the_rows_of_the_timed_region(tmp_path, monkeypatc
               (13.0, '0, 345, 1965, 200.0, 0x0, Not Active, Not Active, Not Active, Not Active')]
     got = s.stop()
     assert got['samples'] == 1 and got['sm_mhz'] == 1935.0 and got['window'].startswith('warm-up') and got['reasons'] == [], got
+
+
+def test_header_documents_every_option():
+    """include/lbm_b200.h is the contract: every option name lbm_set_option accepts is documented there and listed in the
+    error message for an unknown name."""
+    import re
+    src = open(os.path.join(ROOT, 'lattice_boltzmann_parallel_solver_b200', 'csrc', 'lbm_b200.cu')).read()
+    body = src[src.index('extern "C" int lbm_set_option'):src.index('extern "C" int64_t lbm_device_bytes')]
+    names = set(re.findall(r'n == "([a-z0-9_]+)"', body))
+    assert len(names) >= 15, names
+    header = open(os.path.join(ROOT, 'include', 'lbm_b200.h')).read()
+    listed = body[body.index('unknown option'):]
+    for name in sorted(names):
+        assert f'"{name}"' in header, f'option {name} is not documented in include/lbm_b200.h'
+        assert re.search(r'\b' + name + r'\b', listed), f'option {name} is missing from the unknown-option message'
