@@ -1,7 +1,7 @@
 """A CPU stand-in for liblbm_b200.so, for TESTS of the host-side logic only (engine.py, the lazy results of
 lattice_boltzmann_step, the reference's own drivers running on the drop-in modules without a GPU). It implements the
 subset of include/lbm_b200.h those tests reach — stateless operators, contexts with the kind-rule boundary description
-(pull / bounce [- K] / constant / outlet; no pressure-periodic flags) and a self-periodic ghost ring — with the oracle
+(pull / bounce [- K] / constant / outlet, the pressure-periodic source rows) and a self-periodic ghost ring — with the oracle
 as its arithmetic. It is never importable from the product package."""
 import ctypes as C
 
@@ -45,16 +45,61 @@ class FakeLib:
     def lbm_last_error(self):
         return self.err
 
+    @staticmethod
+    def _parse(bc, nx, ny):
+        d = bc._obj if hasattr(bc, '_obj') else bc.contents
+        kinds = [(tuple(d.kinds[k].rule), int(d.kinds[k].flags), int(d.kinds[k].skip_store)) for k in range(d.n_kinds)]
+        return {'kind_map': np.array(np.ctypeslib.as_array(d.kind_map, shape=(nx, ny))),
+                'kinds': kinds,
+                'ktab': np.array(np.ctypeslib.as_array(d.k_table, shape=(d.n_k_rows, 9))),
+                'ctab': np.array(np.ctypeslib.as_array(d.c_table, shape=(d.n_c_rows, 9))) if d.n_c_rows else np.zeros((0, 9)),
+                # pressure-periodic boundary (flags 2 | 4 mark its source rows; skip_store is a device detail)
+                'pbc': (float(d.pbc_rho_in), float(d.pbc_rho_out)) if any(fl & 6 for _, fl, _ in kinds) else None}
+
+    @staticmethod
+    def _apply_pbc(rho_in, rho_out, f_pre, rho, u):
+        """periodic_with_pressure_variations, x variant, in place on f_pre (src/boundary_conditions.py:337-344)."""
+        ly = f_pre.shape[1]
+        feq_m2, feq_p1 = onp.equilibrium(rho[-2], u[-2]), onp.equilibrium(rho[1], u[1])
+        feq_in, feq_out = onp.equilibrium(np.ones(ly) * rho_in, u[-2]), onp.equilibrium(np.ones(ly) * rho_out, u[1])
+        for d in (1, 5, 8):
+            f_pre[0, :, d] = feq_in[:, d] + (f_pre[-2, :, d] - feq_m2[:, d])
+        for d in (3, 6, 7):
+            f_pre[-1, :, d] = feq_out[:, d] + (f_pre[1, :, d] - feq_p1[:, d])
+        return f_pre
+
+    @staticmethod
+    def _apply_rules(desc, f_pre, f_post, f_prev):
+        """The closures' overwrites as data (include/lbm_b200.h): bounce-back (- wall term), inlet constants, outlet copy."""
+        km = desc['kind_map']
+        for k, (rules, flags, skip) in enumerate(desc['kinds']):
+            if k == 0:
+                continue
+            cells = km == k
+            if not cells.any():
+                continue
+            for i, r in enumerate(rules):
+                typ, row = r & 7, r >> 3
+                if typ == 1:      # bounce: f_post[i] = f_pre[opp i] - K[row][opp i]
+                    f_post[cells, i] = np.subtract(f_pre[cells, OPP[i]], desc['ktab'][row][OPP[i]]) if row else f_pre[cells, OPP[i]]
+                elif typ == 2:    # inlet constants
+                    f_post[cells, i] = desc['ctab'][row][i]
+                elif typ == 3:    # outlet: the step's input f of the row before
+                    xs, ys = np.nonzero(cells)
+                    f_post[xs, ys, i] = f_prev[xs - 1, ys, i]
+        return f_post
+
+    def lbm_bc_apply(self, device, nx, ny, bc, f_pre, f_post, f_prev):
+        desc = self._parse(bc, nx, ny)
+        self._apply_rules(desc, _arr(f_pre, (nx, ny, 9)), _arr(f_post, (nx, ny, 9)), _arr(f_prev, (nx, ny, 9)) if f_prev else None)
+        return 0
+
+    def lbm_pbc_apply(self, device, nx, ny, rho_in, rho_out, rho, u, f_pre):
+        self._apply_pbc(rho_in, rho_out, _arr(f_pre, (nx, ny, 9)), _arr(rho, (nx, ny)), _arr(u, (nx, ny, 2)))
+        return 0
+
     def lbm_create(self, device, nx, ny, gx, gy, bc, out):
-        desc = None
-        if bc:
-            d = bc._obj
-            kinds = [(tuple(d.kinds[k].rule), int(d.kinds[k].flags), int(d.kinds[k].skip_store)) for k in range(d.n_kinds)]
-            assert all(fl & ~1 == 0 and sk == 0 for _, fl, sk in kinds), 'the fake has no pressure-periodic boundary'
-            desc = {'kind_map': np.array(np.ctypeslib.as_array(d.kind_map, shape=(nx, ny))),
-                    'kinds': kinds,
-                    'ktab': np.array(np.ctypeslib.as_array(d.k_table, shape=(d.n_k_rows, 9))),
-                    'ctab': np.array(np.ctypeslib.as_array(d.c_table, shape=(d.n_c_rows, 9))) if d.n_c_rows else np.zeros((0, 9))}
+        desc = self._parse(bc, nx, ny) if bc else None
         h = self.next
         self.next += 1
         self.ctxs[h] = _Ctx(nx, ny, (gx, gy), desc)
@@ -98,24 +143,11 @@ class FakeLib:
         if c.ghost != (0, 0):
             assert c.ghost == (1, 1)
             f_pre = onp.self_exchange(f_pre)
+        if c.bc is not None and c.bc['pbc']:
+            f_pre = self._apply_pbc(*c.bc['pbc'], f_pre, rho, u)
         f_post = onp.stream(f_pre)
         if c.bc is not None:
-            km = c.bc['kind_map']
-            for k, (rules, flags, skip) in enumerate(c.bc['kinds']):
-                if k == 0:
-                    continue
-                cells = km == k
-                if not cells.any():
-                    continue
-                for i, r in enumerate(rules):
-                    typ, row = r & 7, r >> 3
-                    if typ == 1:      # bounce: f_post[i] = f_pre[opp i] - K[row][opp i]
-                        f_post[cells, i] = np.subtract(f_pre[cells, OPP[i]], c.bc['ktab'][row][OPP[i]]) if row else f_pre[cells, OPP[i]]
-                    elif typ == 2:    # inlet constants
-                        f_post[cells, i] = c.bc['ctab'][row][i]
-                    elif typ == 3:    # outlet: the step's input f of the row before
-                        xs, ys = np.nonzero(cells)
-                        f_post[xs, ys, i] = f[xs - 1, ys, i]
+            f_post = self._apply_rules(c.bc, f_pre, f_post, f)
         rho2 = onp.density(f_post)
         return f_post, rho2, onp.velocity(rho2, f_post)
 

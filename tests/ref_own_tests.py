@@ -77,8 +77,6 @@ def unit(mode, tree):
     root = set_path(tree, mode)
     import pytest
     args = ['tests', '-q', '-p', 'no:cacheprovider', '-s']
-    if mode == 'fake':
-        args += ['--deselect', 'tests/test_boundary_conditions.py']    # the fake library has no stateless boundary kernels
     rc = pytest.main(args)
     import src.lattice_boltzmann_method as tested       # what the reference's test files import
     assert os.path.dirname(os.path.abspath(tested.__file__)) == os.path.join(root, 'src'), tested.__file__

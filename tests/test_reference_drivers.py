@@ -31,11 +31,8 @@ def _run(mode, out):
     return np.load(out)
 
 
-FAKE_LACKS = {'poiseuille_evolution', 'poiseuille_vectors'}     # tests/fake_native.py has no pressure-periodic boundary; the GPU run has it
-
-
 def _compare(ref, got, what):
-    assert sorted(got.files) == sorted(set(ref.files) - (FAKE_LACKS if what == 'fake native' else set()))
+    assert sorted(got.files) == sorted(ref.files)
     for k in got.files:
         assert ref[k].shape == got[k].shape, (what, k, ref[k].shape, got[k].shape)
         assert np.array_equal(ref[k], got[k], equal_nan=True), \

@@ -40,7 +40,7 @@ def tree(tmp_path_factory):
 
 def test_reference_unit_tests_on_the_dropin_modules_cpu(tree):
     out = _run('unit', 'fake', tree)
-    assert '13 passed, 5 deselected' in out and 'OK unit fake' in out, out[-2000:]
+    assert '18 passed' in out and 'OK unit fake' in out, out[-2000:]
 
 
 def test_reference_parallel_von_karman_test_on_the_dropin_modules_cpu(tree):
