@@ -406,3 +406,31 @@ def test_history_falls_back_to_the_host_without_slots(L, monkeypatch):
     assert sum(1 for x in c.calls if x[0] == 'hist_store') == 4 and c.calls.count(('fields', 1)) == 5
     for a, b in zip(kept, want):
         np.testing.assert_array_equal(a, b)
+
+
+def test_parked_handles_behave_like_arrays(L):
+    """A result parked in the device history is still an ndarray to its owner: cell reads, whole-field reductions, in-place
+    edits (private copy, re-upload when fed back) all work on it after the device has moved on."""
+    lib, P = L.fake, L
+    f, rho, u = start(seed=9)
+    rf, rr, ru = f, rho, u
+    kept_u, kept_rho, want = [], [], []
+    for i in range(6):
+        f, rho, u = P.lattice_boltzmann_step(f, rho, u, 1.2)
+        kept_u.append(u)
+        kept_rho.append(rho)
+        rf, rr, ru = onp.step(rf, rr, ru, 1.2)
+        want.append((rf.copy(), rr.copy(), ru.copy()))
+    np.asarray(f)                                               # the device is at step 6; steps 1-5 are parked
+    assert all(h._hist is not None for h in kept_u[:5] + kept_rho[:5])
+    assert np.array_equal(kept_u[1][3, 4, ...], want[1][2][3, 4]) and kept_rho[2][5, 6] == want[2][1][5, 6]
+    assert np.amax(kept_rho[3]) == want[3][1].max() and kept_u[3].min() == want[3][2].min()
+    assert (kept_u[0] + 1.0).shape == (12, 10, 2) and np.array_equal(kept_u[0] * 2.0, want[0][2] * 2.0)
+    h = kept_u[4]
+    h[0, 0, 0] = 7.0                                            # in-place edit of a parked result: a private host copy
+    assert h._dirty and h[0, 0, 0] == 7.0 and np.array_equal(np.asarray(h)[1:], want[4][2][1:])
+    # feeding an old, edited state back uploads it (the reference's arrays are plain values)
+    edited_u = np.asarray(h).copy()
+    f2, rho2, u2 = P.lattice_boltzmann_step(np.asarray(want[4][0]), kept_rho[4], h, 1.2)
+    ref2 = onp.step(want[4][0], want[4][1], edited_u, 1.2)
+    assert np.array_equal(np.asarray(f2), ref2[0]) and np.array_equal(np.asarray(u2), ref2[2])
